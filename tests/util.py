@@ -1,0 +1,93 @@
+"""Shared helpers for the parity tests: golden loading, oracle drivers, metrics."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+EULER_CASES = ["euler40", "vortex", "vortex_triangle", "disc_island", "xper_noslip",
+               "euler_enrk3_upwind", "euler_centered_ef", "euler_cweno"]
+ALL_CASES = EULER_CASES + ["rsw", "rsw_islands", "qgrsw_topo", "qgrsw_islands",
+                           "warm_bubble", "lock_exchange"]
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN, f"case_{name}.npz"))
+        self.meta = json.loads(str(self.z["meta"]))
+        self.param = self.meta["param"]
+        self.dts = self.meta["dts"]
+        self.nsteps = self.meta["nsteps"]
+        self.msk = self.z["msk"]
+        self.hb = self.z["hb"] if "hb" in self.z.files else None
+
+    def fields(self, tag):
+        pre = tag + "/"
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
+
+
+def set_state(state, fields):
+    """Copy a {name or name.x: array} dict into a namespace/namedtuple state in place."""
+    for k, v in fields.items():
+        if "." in k:
+            n, c = k.split(".")
+            getattr(getattr(state, n), c)[...] = v
+        else:
+            getattr(state, k)[...] = v
+
+
+def get_state(state, names):
+    out = {}
+    for k in names:
+        if "." in k:
+            n, c = k.split(".")
+            out[k] = getattr(getattr(state, n), c)
+        else:
+            out[k] = getattr(state, k)
+    return out
+
+
+def oracle_model(orc, g):
+    p = orc.make_param(**g.param)
+    m = orc.Model(p, msk=g.msk.copy())
+    if g.hb is not None:
+        m.mesh.hb = g.hb.copy()
+    set_state(m.state, g.fields("init"))
+    return m
+
+
+def rel_l2(a, b, w=None):
+    """relative L2 of a-b against b over the cells where w != 0 (finite entries only)."""
+    if w is None:
+        w = np.ones(a.shape, dtype=bool)
+    k = (np.asarray(w) != 0) & np.isfinite(b)
+    d = a[k] - b[k]
+    nb = np.sqrt(np.sum(b[k] ** 2))
+    if nb == 0:
+        return float(np.sqrt(np.sum(d ** 2)))
+    return float(np.sqrt(np.sum(d ** 2)) / nb)
+
+
+def remove_component_means(p, msk):
+    """p minus its mean over each connected fluid component (Neumann null space)."""
+    from scipy import ndimage
+    lab, n = ndimage.label(msk != 0)
+    q = p.copy()
+    for c in range(1, n + 1):
+        k = lab == c
+        q[k] -= q[k].mean()
+    return q
+
+
+def field_mask(mesh, name):
+    """which cells count for the parity metric of a given field."""
+    base = name.split(".")[0]
+    if name.endswith(".x"):
+        return mesh.mskx
+    if name.endswith(".y"):
+        return mesh.msky
+    if base in ("omega", "pv", "psi"):
+        return mesh.mskv
+    return mesh.msk
