@@ -1,0 +1,136 @@
+// Internal structures shared by the translation units of libf2d.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/f2d.h"
+
+namespace f2d {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define F2D_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return f2d::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define F2D_TRY(call)                  \
+    do {                               \
+        int _s = (call);               \
+        if (_s != F2D_OK) return _s;   \
+    } while (0)
+
+// mask bits of the fine multigrid level (one byte per grid point)
+enum : uint8_t {
+    NB_SELF = 1,   // the point is an unknown
+    NB_W = 2, NB_E = 4, NB_S = 8, NB_N = 16,   // coupling to that neighbour is open
+    NB_PJ = 32,    // coarse parent (Jn, I0) is fluid      (prolongation weights)
+    NB_PI = 64,    //               (J0, In)
+    NB_PJI = 128   //               (Jn, In)
+};
+
+// Fine level: a window of the reference-layout (n2, n1) arrays.
+struct FineView {
+    int ny, nx;        // logical size of the window
+    int oj, oi;        // array coordinates of logical (0,0); may be negative
+    int n2, n1;        // array shape
+    int periodic;      // x wraps inside the window
+    int dirichlet;     // vertices: fixed diagonal; centres: Neumann
+    double cx, cy;     // dy/dx, dx/dy   (elliptic.py:138-139)
+    double shift;      // maindiag       (elliptic.py:186-190)
+    const uint8_t *nb;
+};
+
+// Coarse level l >= 1: halo-padded arrays (ny+2) x pitch, element (J,I) at
+// (J+1)*pitch + I+1.
+struct CoarseView {
+    int ny, nx, pitch;
+    int periodic;
+    int dirichlet;
+    const double *cx;     // coupling across the west face of (J,I)
+    const double *cy;     // coupling across the south face
+    const double *dinv;   // 1/diagonal, 0 where not an unknown
+    const uint8_t *code;  // NB_SELF | NB_P* bits
+};
+
+struct Level {
+    int ny = 0, nx = 0, pitch = 0;
+    size_t n = 0;                       // (ny+2)*pitch
+    double *x = nullptr, *b = nullptr, *r = nullptr;
+    double *cx = nullptr, *cy = nullptr, *dinv = nullptr;
+    double *mass = nullptr, *wall = nullptr;   // set-up only
+    uint8_t *code = nullptr;
+};
+
+struct Multigrid {
+    bool built = false;
+    int which = 0;
+    FineView fine{};
+    uint8_t *nb = nullptr;            // fine bits, (n2,n1)
+    std::vector<Level> lev;           // lev[0] unused except sizes; lev[l>=1] coarse
+    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr;   // CG vectors (n2,n1)
+    int64_t nunknown = 0;
+};
+
+}  // namespace f2d
+
+struct f2d_ctx {
+    f2d_config cfg{};
+    int n1 = 0, n2 = 0, nh = 0;
+    size_t n = 0;
+    double dx = 0, dy = 0, area = 0, idx2 = 0, idy2 = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    int nsm = 148;
+
+    // mesh (int8, (n2,n1))
+    std::map<std::string, int8_t *> mesh;
+    bool mesh_ready = false;
+    // state + scratch (float64, (n2,n1))
+    std::map<std::string, double *> fields;
+    std::vector<std::string> prognostic;     // leaf names, e.g. "u.x","u.y"
+    int nstages = 3;
+    double *hb = nullptr;                    // topography (zeros by default)
+    double *tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // work arrays (n2,n1)
+
+    f2d::Multigrid mg[3];
+    // reductions
+    double *d_scal = nullptr;       // device scalars
+    double *d_part = nullptr;       // per-block partial sums
+    unsigned int *d_count = nullptr;
+    double *h_scal = nullptr;       // pinned mirror
+    // solver statistics
+    int64_t nsolves = 0, niters = 0;
+    double max_relres = 0;
+
+    int8_t *m(const char *k) { return mesh.at(k); }
+    double *f(const std::string &k) { return fields.at(k); }
+    bool has(const std::string &k) const { return fields.count(k) != 0; }
+};
+
+namespace f2d {
+// ops.cu
+int build_mesh(f2d_ctx *c, const int8_t *h_msk);
+int op_fill(f2d_ctx *c, double *a);
+// step.cu
+int model_rhs(f2d_ctx *c, int k);
+int model_addto(f2d_ctx *c, int ncoef, const double *coefs);
+int model_diag(f2d_ctx *c);
+int model_step(f2d_ctx *c, double dt, int nsteps);
+int max_abs_U(f2d_ctx *c, double *out);
+// mg.cu
+int mg_build(f2d_ctx *c, int which);
+void mg_free(f2d_ctx *c, int which);
+int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters,
+             double *relres);
+int mg_apply(f2d_ctx *c, int which, const double *x, double *y);
+int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
+int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
+}  // namespace f2d

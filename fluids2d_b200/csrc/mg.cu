@@ -1,0 +1,925 @@
+// Matrix-free masked geometric multigrid for the reference's 5-point operators
+// (elliptic.py:114-195), used as a CG preconditioner or as a stand-alone
+// V-cycle iteration.  It replaces Poisson2D's SuperLU factorisation
+// (elliptic.py:78, :83).
+//
+//   operator   L = -A (symmetric positive semi-definite):
+//              (L x)_P = diag_P x_P - sum_nb c_nb x_nb,
+//              c = dy/dx (W,E), dx/dy (S,N) across open faces,
+//              diag = sum(open c) + maindiag            cell centres, Neumann
+//              diag = 2(dy/dx + dx/dy) + maindiag       vertices, Dirichlet
+//   fine level operates in place on the reference-layout (n2,n1) arrays, one
+//              byte of mask bits per point (no coefficient arrays);
+//   coarsening 2x2 aggregation of cells; coarse couplings are half the sum of
+//              the fine couplings crossing the coarse face (rediscretisation
+//              on masked grids), mass terms add up;
+//   transfer   mask-renormalised bilinear prolongation P (weights 9,3,3,1 over
+//              the fluid parents, so constants are preserved next to walls),
+//              restriction R = P^T  -> symmetric V-cycle, valid CG preconditioner;
+//   smoother   red-black Gauss-Seidel, nu1 sweeps (R,B) down, nu2 (B,R) up.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.cuh"
+#include "reduce.cuh"
+
+namespace f2d {
+
+#define LAUNCH_CHECK(c)                 \
+    do {                                \
+        (c)->launches++;                \
+        F2D_CUDA(cudaGetLastError());   \
+    } while (0)
+
+// device scalar slots
+enum { S_RR = 0, S_FF = 1, S_RZ = 2, S_PQ = 3, S_RZNEW = 4, S_TMP = 5 };
+
+// ------------------------------------------------------------------ helpers --
+__device__ __forceinline__ bool fine_index(const FineView &F, int j, int i, long &idx) {
+    int aj = F.oj + j, ai = F.oi + i;
+    if (aj < 0 || aj >= F.n2 || ai < 0 || ai >= F.n1) return false;
+    idx = (long)aj * F.n1 + ai;
+    return true;
+}
+
+struct Stencil {
+    double cw, ce, cs, cn, diag;
+    long iw, ie, is, in;
+};
+
+__device__ __forceinline__ Stencil fine_stencil(const FineView &F, int i, long idx, uint8_t c) {
+    Stencil s;
+    s.cw = (c & NB_W) ? F.cx : 0.0;
+    s.ce = (c & NB_E) ? F.cx : 0.0;
+    s.cs = (c & NB_S) ? F.cy : 0.0;
+    s.cn = (c & NB_N) ? F.cy : 0.0;
+    s.diag = F.dirichlet ? (2.0 * (F.cx + F.cy) + F.shift) : (((s.cw + s.ce) + s.cs) + s.cn + F.shift);
+    s.iw = idx - 1;
+    s.ie = idx + 1;
+    if (F.periodic) {
+        if (i == 0) s.iw = idx + (F.nx - 1);
+        if (i == F.nx - 1) s.ie = idx - (F.nx - 1);
+    }
+    s.is = idx - F.n1;
+    s.in = idx + F.n1;
+    return s;
+}
+
+// sum_nb c_nb x_nb with closed faces skipped (their neighbours may hold anything)
+__device__ __forceinline__ double fine_offdiag(const Stencil &s, uint8_t c, const double *__restrict__ x) {
+    double a = 0.0;
+    if (c & NB_W) a += s.cw * x[s.iw];
+    if (c & NB_E) a += s.ce * x[s.ie];
+    if (c & NB_S) a += s.cs * x[s.is];
+    if (c & NB_N) a += s.cn * x[s.in];
+    return a;
+}
+
+// normaliser of the prolongation weights.  Neumann: renormalise over the fluid
+// parents (constants are interpolated exactly next to walls).  Dirichlet: a
+// masked parent IS the wall value 0, so the plain bilinear weights stand.
+__device__ __forceinline__ double w16_of(uint8_t c, int dirichlet) {
+    if (dirichlet) return 16.0;
+    return (double)(9 + ((c & NB_PJ) ? 3 : 0) + ((c & NB_PI) ? 3 : 0) + ((c & NB_PJI) ? 1 : 0));
+}
+
+__device__ __forceinline__ void coarse_idx(const CoarseView &V, int J, int I, long &c, long &w,
+                                           long &e, long &s, long &n) {
+    c = (long)(J + 1) * V.pitch + I + 1;
+    w = c - 1;
+    e = c + 1;
+    if (V.periodic) {
+        if (I == 0) w = c + (V.nx - 1);
+        if (I == V.nx - 1) e = c - (V.nx - 1);
+    }
+    s = c - V.pitch;
+    n = c + V.pitch;
+}
+
+// parents of a fine cell (logical j,i): own aggregate (J0,I0) and the next
+// nearest in each direction; returns false for a parent outside the grid
+__device__ __forceinline__ void parents(int j, int i, int &J0, int &Jn, int &I0, int &In) {
+    J0 = j >> 1;
+    Jn = J0 + ((j & 1) ? 1 : -1);
+    I0 = i >> 1;
+    In = I0 + ((i & 1) ? 1 : -1);
+}
+
+// -------------------------------------------------------------- fine level --
+template <bool ZERO_GUESS>
+__global__ void __launch_bounds__(256)
+k_smooth0(FineView F, double *__restrict__ x, const double *__restrict__ f, double fscale, int color) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.nx || j >= F.ny || ((i + j) & 1) != color) return;
+    long idx;
+    if (!fine_index(F, j, i, idx)) return;
+    uint8_t c = F.nb[idx];
+    if (!(c & NB_SELF)) return;
+    Stencil s = fine_stencil(F, i, idx, c);
+    if (s.diag <= 0.0) return;
+    double a = ZERO_GUESS ? 0.0 : fine_offdiag(s, c, x);
+    x[idx] = (fscale * f[idx] + a) / s.diag;
+}
+
+// r~ = (f - L x) / W16   (pre-scaled for the R = P^T gather)
+__global__ void __launch_bounds__(256)
+k_resid0(FineView F, const double *__restrict__ x, const double *__restrict__ f, double fscale,
+         double *__restrict__ r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.nx || j >= F.ny) return;
+    long idx;
+    if (!fine_index(F, j, i, idx)) return;
+    uint8_t c = F.nb[idx];
+    if (!(c & NB_SELF)) return;
+    Stencil s = fine_stencil(F, i, idx, c);
+    double res = fscale * f[idx] - (s.diag * x[idx] - fine_offdiag(s, c, x));
+    r[idx] = res / w16_of(c, F.dirichlet);
+}
+
+// b_c = sum over the 4x4 fine cells around the aggregate of wy*wx*r~
+__global__ void __launch_bounds__(256)
+k_restrict0(FineView F, const double *__restrict__ r, CoarseView C, double *__restrict__ bc) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= C.nx || J >= C.ny) return;
+    long cc = (long)(J + 1) * C.pitch + I + 1;
+    if (!(C.code[cc] & NB_SELF)) { bc[cc] = 0.0; return; }
+    double acc = 0.0;
+#pragma unroll
+    for (int a = -1; a <= 2; a++) {
+        int j = 2 * J + a;
+        if (j < 0 || j >= F.ny) continue;
+        double wy = (a == 0 || a == 1) ? 3.0 : 1.0;
+#pragma unroll
+        for (int b = -1; b <= 2; b++) {
+            int i = 2 * I + b;
+            if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            else if (i < 0 || i >= F.nx) continue;
+            double wx = (b == 0 || b == 1) ? 3.0 : 1.0;
+            long idx;
+            if (!fine_index(F, j, i, idx)) continue;
+            if (F.nb[idx] & NB_SELF) acc += wy * wx * r[idx];
+        }
+    }
+    bc[cc] = acc;
+}
+
+// x_f += (9 x00 + 3 xn0 + 3 x0n + xnn) / W16
+__global__ void __launch_bounds__(256)
+k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const double *__restrict__ xc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.nx || j >= F.ny) return;
+    long idx;
+    if (!fine_index(F, j, i, idx)) return;
+    uint8_t c = F.nb[idx];
+    if (!(c & NB_SELF)) return;
+    int J0, Jn, I0, In;
+    parents(j, i, J0, Jn, I0, In);
+    if (C.periodic) { if (In < 0) In += C.nx; else if (In >= C.nx) In -= C.nx; }
+    long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;   // halo rows absorb Jn=-1, ny
+    double v = 9.0 * xc[r0 + I0 + 1];
+    if (c & NB_PJ) v += 3.0 * xc[rn + I0 + 1];
+    if (c & NB_PI) v += 3.0 * xc[r0 + In + 1];
+    if (c & NB_PJI) v += xc[rn + In + 1];
+    x[idx] += v / w16_of(c, F.dirichlet);
+}
+
+// 1-D grid-stride walk over the fine window (for kernels with reductions)
+#define FINE_LOOP(F)                                                              \
+    long _n0 = (long)(F).ny * (F).nx;                                             \
+    for (long _t = (long)blockIdx.x * blockDim.x + threadIdx.x; _t < _n0;         \
+         _t += (long)gridDim.x * blockDim.x)
+
+// r = f - L x ; rr = r.r ; ff = f.f            (CG start / convergence check)
+__global__ void __launch_bounds__(256)
+k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ f, double fscale,
+           double *__restrict__ r, double *part, unsigned int *count, double *out) {
+    double v[2] = {0.0, 0.0};
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        uint8_t c = F.nb[idx];
+        if (!(c & NB_SELF)) continue;
+        Stencil s = fine_stencil(F, i, idx, c);
+        double ff = fscale * f[idx];
+        double res = ff - (s.diag * x[idx] - fine_offdiag(s, c, x));
+        if (r) r[idx] = res;
+        v[0] += res * res;
+        v[1] += ff * ff;
+    }
+    grid_reduce<OpSum, 2>(v, part, count, out);
+}
+
+// q = L p ; pq = p.q
+__global__ void __launch_bounds__(256)
+k_cg_apply(FineView F, const double *__restrict__ p, double *__restrict__ q, double *part,
+           unsigned int *count, double *out) {
+    double v[1] = {0.0};
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        uint8_t c = F.nb[idx];
+        if (!(c & NB_SELF)) continue;
+        Stencil s = fine_stencil(F, i, idx, c);
+        double pv = p[idx];
+        double qv = s.diag * pv - fine_offdiag(s, c, p);
+        q[idx] = qv;
+        v[0] += pv * qv;
+    }
+    grid_reduce<OpSum, 1>(v, part, count, out);
+}
+
+// x += alpha p ; r -= alpha q ; rr = r.r          alpha = rz / pq
+__global__ void __launch_bounds__(256)
+k_cg_update(FineView F, double *__restrict__ x, double *__restrict__ r,
+            const double *__restrict__ p, const double *__restrict__ q,
+            const double *__restrict__ scal, double *part, unsigned int *count, double *out) {
+    double pq = scal[S_PQ];
+    double alpha = pq != 0.0 ? scal[S_RZ] / pq : 0.0;
+    double v[1] = {0.0};
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        if (!(F.nb[idx] & NB_SELF)) continue;
+        x[idx] += alpha * p[idx];
+        double rv = r[idx] - alpha * q[idx];
+        r[idx] = rv;
+        v[0] += rv * rv;
+    }
+    grid_reduce<OpSum, 1>(v, part, count, out);
+}
+
+// out = a.b over the unknowns
+__global__ void __launch_bounds__(256)
+k_dot(FineView F, const double *__restrict__ a, const double *__restrict__ b, double *part,
+      unsigned int *count, double *out) {
+    double v[1] = {0.0};
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        if (!(F.nb[idx] & NB_SELF)) continue;
+        v[0] += a[idx] * b[idx];
+    }
+    grid_reduce<OpSum, 1>(v, part, count, out);
+}
+
+// p = z + beta p, beta = rz_new / rz (first: p = z); then rz <- rz_new
+__global__ void __launch_bounds__(256)
+k_cg_dir(FineView F, double *__restrict__ p, const double *__restrict__ z,
+         const double *__restrict__ scal, int first) {
+    double beta = 0.0;
+    if (!first) { double rz = scal[S_RZ]; beta = rz != 0.0 ? scal[S_RZNEW] / rz : 0.0; }
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        if (!(F.nb[idx] & NB_SELF)) continue;
+        p[idx] = first ? z[idx] : z[idx] + beta * p[idx];
+    }
+}
+__global__ void k_cg_shift(double *scal) { scal[S_RZ] = scal[S_RZNEW]; }
+
+// y = A x = -L x on the unknowns, 0 elsewhere inside the window
+__global__ void __launch_bounds__(256)
+k_apply_A(FineView F, const double *__restrict__ x, double *__restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.nx || j >= F.ny) return;
+    long idx;
+    if (!fine_index(F, j, i, idx)) return;
+    uint8_t c = F.nb[idx];
+    if (!(c & NB_SELF)) return;
+    Stencil s = fine_stencil(F, i, idx, c);
+    y[idx] = fine_offdiag(s, c, x) - s.diag * x[idx];
+}
+
+// ------------------------------------------------------------ coarse levels --
+template <bool ZERO_GUESS>
+__global__ void __launch_bounds__(256)
+k_smooth(CoarseView V, double *__restrict__ x, const double *__restrict__ b, int color) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= V.nx || J >= V.ny || ((I + J) & 1) != color) return;
+    long c, w, e, s, n;
+    coarse_idx(V, J, I, c, w, e, s, n);
+    double di = V.dinv[c];
+    if (di == 0.0) return;
+    double a = 0.0;
+    if (!ZERO_GUESS) a = V.cx[c] * x[w] + V.cx[e] * x[e] + V.cy[c] * x[s] + V.cy[n] * x[n];
+    x[c] = (b[c] + a) * di;
+}
+
+__global__ void __launch_bounds__(256)
+k_resid(CoarseView V, const double *__restrict__ x, const double *__restrict__ b,
+        double *__restrict__ r) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= V.nx || J >= V.ny) return;
+    long c, w, e, s, n;
+    coarse_idx(V, J, I, c, w, e, s, n);
+    double di = V.dinv[c];
+    if (di == 0.0) { r[c] = 0.0; return; }
+    double a = V.cx[c] * x[w] + V.cx[e] * x[e] + V.cy[c] * x[s] + V.cy[n] * x[n];
+    double res = b[c] - (x[c] / di - a);
+    r[c] = res / w16_of(V.code[c], V.dirichlet);
+}
+
+__global__ void __launch_bounds__(256)
+k_restrict(CoarseView Vf, const double *__restrict__ r, CoarseView C, double *__restrict__ bc) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= C.nx || J >= C.ny) return;
+    long cc = (long)(J + 1) * C.pitch + I + 1;
+    if (!(C.code[cc] & NB_SELF)) { bc[cc] = 0.0; return; }
+    double acc = 0.0;
+#pragma unroll
+    for (int a = -1; a <= 2; a++) {
+        int j = 2 * J + a;
+        if (j < 0 || j >= Vf.ny) continue;
+        double wy = (a == 0 || a == 1) ? 3.0 : 1.0;
+#pragma unroll
+        for (int b = -1; b <= 2; b++) {
+            int i = 2 * I + b;
+            if (Vf.periodic) { if (i < 0) i += Vf.nx; else if (i >= Vf.nx) i -= Vf.nx; }
+            else if (i < 0 || i >= Vf.nx) continue;
+            double wx = (b == 0 || b == 1) ? 3.0 : 1.0;
+            acc += wy * wx * r[(long)(j + 1) * Vf.pitch + i + 1];   // r~ is 0 off the unknowns
+        }
+    }
+    bc[cc] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+k_prolong(CoarseView Vf, double *__restrict__ x, CoarseView C, const double *__restrict__ xc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Vf.nx || j >= Vf.ny) return;
+    long idx = (long)(j + 1) * Vf.pitch + i + 1;
+    uint8_t c = Vf.code[idx];
+    if (!(c & NB_SELF)) return;
+    int J0, Jn, I0, In;
+    parents(j, i, J0, Jn, I0, In);
+    if (C.periodic) { if (In < 0) In += C.nx; else if (In >= C.nx) In -= C.nx; }
+    long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;
+    double v = 9.0 * xc[r0 + I0 + 1];
+    if (c & NB_PJ) v += 3.0 * xc[rn + I0 + 1];
+    if (c & NB_PI) v += 3.0 * xc[r0 + In + 1];
+    if (c & NB_PJI) v += xc[rn + In + 1];
+    x[idx] += v / w16_of(c, Vf.dirichlet);
+}
+
+// coarsest level: nsw sweeps (R,B) then nsw sweeps (B,R) from a zero guess, one CTA
+__global__ void __launch_bounds__(1024)
+k_coarsest(CoarseView V, double *__restrict__ x, const double *__restrict__ b, int nsw) {
+    int npts = V.ny * V.nx;
+    for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+        int J = t / V.nx, I = t - J * V.nx;
+        x[(long)(J + 1) * V.pitch + I + 1] = 0.0;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < 4 * nsw; sweep++) {
+        int color = (sweep < 2 * nsw) ? (sweep & 1) : 1 - (sweep & 1);
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int J = t / V.nx, I = t - J * V.nx;
+            if (((I + J) & 1) != color) continue;
+            long c, w, e, s, n;
+            coarse_idx(V, J, I, c, w, e, s, n);
+            double di = V.dinv[c];
+            if (di == 0.0) continue;
+            double a = V.cx[c] * x[w] + V.cx[e] * x[e] + V.cy[c] * x[s] + V.cy[n] * x[n];
+            x[c] = (b[c] + a) * di;
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------- set-up ---
+// solver mask -> fine bits (elliptic.py:102-111, :144-165 neighbour rules)
+__global__ void k_build_nb(FineView F, const int8_t *__restrict__ sm, uint8_t *__restrict__ nb) {
+    int ai = blockIdx.x * blockDim.x + threadIdx.x;
+    int aj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ai >= F.n1 || aj >= F.n2) return;
+    long idx = (long)aj * F.n1 + ai;
+    uint8_t c = 0;
+    int i = ai - F.oi;
+    bool inwin = i >= 0 && i < F.nx;
+    if (inwin && sm[idx]) {
+        c = NB_SELF;
+        long iw = idx - 1, ie = idx + 1;
+        bool hw = ai > 0, he = ai < F.n1 - 1;
+        if (F.periodic) {
+            if (i == 0) iw = idx + (F.nx - 1);
+            if (i == F.nx - 1) ie = idx - (F.nx - 1);
+            hw = he = true;
+        } else {
+            hw = hw && i > 0;
+            he = he && i < F.nx - 1;
+        }
+        if (hw && sm[iw]) c |= NB_W;
+        if (he && sm[ie]) c |= NB_E;
+        if (aj > 0 && sm[idx - F.n1]) c |= NB_S;
+        if (aj < F.n2 - 1 && sm[idx + F.n1]) c |= NB_N;
+    }
+    nb[idx] = c;
+}
+
+// level 0 -> level 1 coefficients
+// Dirichlet wall couplings: the aggregate centre of level l sits (2^l+1)/2 fine
+// spacings from the wall, so the coupling shrinks by (2^(l-1)+1)/(2^l+1) per
+// level (2/3, 3/5, 5/9, ... -> 1/2) instead of the 1/2 of interior faces.
+__global__ void k_coarsen0(FineView F, Level L1, int periodic, double wallfac) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= L1.nx || J >= L1.ny) return;
+    long cc = (long)(J + 1) * L1.pitch + I + 1;
+    double cx = 0, cy = 0, mass = 0, wall = 0;
+    int fluid = 0;
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            int j = 2 * J + a, i = 2 * I + b;
+            if (j >= F.ny || i >= F.nx) continue;
+            long idx;
+            if (!fine_index(F, j, i, idx)) continue;
+            uint8_t c = F.nb[idx];
+            if (!(c & NB_SELF)) continue;
+            fluid = 1;
+            if (b == 0 && (c & NB_W)) cx += F.cx;
+            if (a == 0 && (c & NB_S)) cy += F.cy;
+            mass += F.shift;
+            if (F.dirichlet)
+                wall += F.cx * (2 - ((c & NB_W) ? 1 : 0) - ((c & NB_E) ? 1 : 0)) +
+                        F.cy * (2 - ((c & NB_S) ? 1 : 0) - ((c & NB_N) ? 1 : 0));
+        }
+    L1.cx[cc] = 0.5 * cx;
+    L1.cy[cc] = 0.5 * cy;
+    L1.mass[cc] = mass;
+    L1.wall[cc] = wallfac * wall;
+    L1.code[cc] = fluid ? NB_SELF : 0;
+}
+
+// level l -> l+1 coefficients (l >= 1)
+__global__ void k_coarsen(Level Lf, Level Lc, int periodic, double wallfac) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= Lc.nx || J >= Lc.ny) return;
+    long cc = (long)(J + 1) * Lc.pitch + I + 1;
+    double cx = 0, cy = 0, mass = 0, wall = 0;
+    int fluid = 0;
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            int j = 2 * J + a, i = 2 * I + b;
+            if (j >= Lf.ny || i >= Lf.nx) continue;
+            long idx = (long)(j + 1) * Lf.pitch + i + 1;
+            if (!(Lf.code[idx] & NB_SELF)) continue;
+            fluid = 1;
+            if (b == 0) cx += Lf.cx[idx];
+            if (a == 0) cy += Lf.cy[idx];
+            mass += Lf.mass[idx];
+            wall += Lf.wall[idx];
+        }
+    Lc.cx[cc] = 0.5 * cx;
+    Lc.cy[cc] = 0.5 * cy;
+    Lc.mass[cc] = mass;
+    Lc.wall[cc] = wallfac * wall;
+    Lc.code[cc] = fluid ? NB_SELF : 0;
+}
+
+__global__ void k_build_dinv(Level L, int periodic) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= L.nx || J >= L.ny) return;
+    long c = (long)(J + 1) * L.pitch + I + 1;
+    long e = c + 1;
+    if (periodic && I == L.nx - 1) e = c - (L.nx - 1);
+    double d = 0.0;
+    if (L.code[c] & NB_SELF) {
+        double diag = L.cx[c] + L.cx[e] + L.cy[c] + L.cy[c + L.pitch] + L.mass[c] + L.wall[c];
+        d = diag > 0.0 ? 1.0 / diag : 0.0;
+    }
+    L.dinv[c] = d;
+    if (d == 0.0) L.code[c] = 0;
+}
+
+// which of the three non-own parents of each fine cell are unknowns on the coarse level
+__device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, int periodic) {
+    int J0, Jn, I0, In;
+    parents(j, i, J0, Jn, I0, In);
+    bool jin = Jn >= 0 && Jn < Lc.ny, iin = true;
+    if (periodic) { if (In < 0) In += Lc.nx; else if (In >= Lc.nx) In -= Lc.nx; }
+    else iin = In >= 0 && In < Lc.nx;
+    uint8_t c = 0;
+    if (jin && (Lc.code[(long)(Jn + 1) * Lc.pitch + I0 + 1] & NB_SELF)) c |= NB_PJ;
+    if (iin && (Lc.code[(long)(J0 + 1) * Lc.pitch + In + 1] & NB_SELF)) c |= NB_PI;
+    if (jin && iin && (Lc.code[(long)(Jn + 1) * Lc.pitch + In + 1] & NB_SELF)) c |= NB_PJI;
+    return c;
+}
+
+__global__ void k_parent_bits0(FineView F, uint8_t *__restrict__ nb, Level Lc, int periodic) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.nx || j >= F.ny) return;
+    long idx;
+    if (!fine_index(F, j, i, idx)) return;
+    uint8_t c = nb[idx];
+    if (!(c & NB_SELF)) return;
+    nb[idx] = c | parent_bits(j, i, Lc, periodic);
+}
+
+__global__ void k_parent_bits(Level Lf, Level Lc, int periodic) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= Lf.nx || j >= Lf.ny) return;
+    long idx = (long)(j + 1) * Lf.pitch + i + 1;
+    uint8_t c = Lf.code[idx];
+    if (!(c & NB_SELF)) return;
+    Lf.code[idx] = c | parent_bits(j, i, Lc, periodic);
+}
+
+__global__ void k_solver_mask(const int8_t *__restrict__ m, int8_t *__restrict__ sm, int n2, int n1,
+                              int nh, int xper) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= n1) return;
+    long k = (long)j * n1 + i;
+    int8_t v = m[k] != 0;
+    if (xper && (i < nh || i >= n1 - nh)) v = 0;
+    sm[k] = v;
+}
+
+// ------------------------------------------------------------------- host ---
+static dim3 blk() { return dim3(64, 4); }
+static dim3 grd(int nx, int ny) { return dim3((nx + 63) / 64, (ny + 3) / 4); }
+
+static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
+    CoarseView V;
+    V.ny = L.ny; V.nx = L.nx; V.pitch = L.pitch; V.periodic = periodic;
+    V.cx = L.cx; V.cy = L.cy; V.dinv = L.dinv; V.code = L.code;
+    V.dirichlet = dirichlet;
+    return V;
+}
+
+void mg_free(f2d_ctx *c, int which) {
+    Multigrid &M = c->mg[which];
+    cudaFree(M.nb);
+    for (double *p : {M.r, M.z, M.p, M.q}) cudaFree(p);
+    for (Level &L : M.lev) {
+        for (double *p : {L.x, L.b, L.r, L.cx, L.cy, L.dinv, L.mass, L.wall}) cudaFree(p);
+        cudaFree(L.code);
+    }
+    M = Multigrid();
+}
+
+int mg_build(f2d_ctx *c, int which) {
+    mg_free(c, which);
+    Multigrid &M = c->mg[which];
+    M.which = which;
+    const int n1 = c->n1, n2 = c->n2, nh = c->nh;
+    const int xper = c->cfg.xperiodic;
+    const bool vert = which != F2D_SOLVER_CENTERS;
+
+    // solver mask and its bounding box
+    int8_t *sm;
+    F2D_CUDA(cudaMalloc(&sm, c->n));
+    k_solver_mask<<<dim3((n1 + 127) / 128, n2), 128, 0, c->stream>>>(c->m(vert ? "mskv" : "msk"), sm,
+                                                                      n2, n1, nh, xper);
+    LAUNCH_CHECK(c);
+    std::vector<int8_t> h(c->n);
+    F2D_CUDA(cudaMemcpyAsync(h.data(), sm, c->n, cudaMemcpyDeviceToHost, c->stream));
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    int jmin = n2, jmax = -1, imin = n1, imax = -1;
+    int64_t cnt = 0;
+    for (int j = 0; j < n2; j++)
+        for (int i = 0; i < n1; i++)
+            if (h[(size_t)j * n1 + i]) {
+                cnt++;
+                jmin = std::min(jmin, j); jmax = std::max(jmax, j);
+                imin = std::min(imin, i); imax = std::max(imax, i);
+            }
+    M.nunknown = cnt;
+    FineView &F = M.fine;
+    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.dirichlet = vert;
+    F.cx = c->dy / c->dx; F.cy = c->dx / c->dy;
+    F.shift = (which == F2D_SOLVER_HELMHOLTZ) ? c->area * c->cfg.f0 * c->cfg.f0 / (c->cfg.g * c->cfg.H) : 0.0;
+    if (cnt == 0) {
+        cudaFree(sm);
+        F.ny = F.nx = 0; F.oj = F.oi = 0;
+        M.built = true;
+        return F2D_OK;
+    }
+    // origin aligned with the interior corner (nh, nh) so that power-of-two
+    // interiors aggregate cleanly; pushed out by a power of two if fluid
+    // extends into the halo (the reference's yperiodic quirk, SURVEY note Y)
+    auto origin = [&](int lo) {
+        int o = nh;
+        int span = 1;
+        while (o > lo) { o = nh - span; span *= 2; }
+        return o;
+    };
+    F.oj = origin(jmin);
+    F.ny = jmax + 1 - F.oj;
+    if (xper) { F.oi = nh; F.nx = c->cfg.nx; }
+    else { F.oi = origin(imin); F.nx = imax + 1 - F.oi; }
+
+    F2D_CUDA(cudaMalloc(&M.nb, c->n));
+    F.nb = M.nb;
+    k_build_nb<<<grd(n1, n2), blk(), 0, c->stream>>>(F, sm, M.nb);
+    LAUNCH_CHECK(c);
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(sm);
+
+    // level sizes
+    std::vector<std::pair<int, int>> sizes;
+    sizes.push_back({F.ny, F.nx});
+    while (true) {
+        int ny = sizes.back().first, nx = sizes.back().second;
+        if ((long)ny * nx <= 16 || sizes.size() >= 24) break;
+        if (xper && (nx & 1)) break;
+        if (ny == 1 && nx == 1) break;
+        sizes.push_back({(ny + 1) / 2, xper ? nx / 2 : (nx + 1) / 2});
+    }
+    if (sizes.size() < 2) {
+        if (xper && (F.nx & 1)) {
+            set_error("x-periodic elliptic solve needs an even nx (got %d)", F.nx);
+            return F2D_ERR_UNSUPPORTED;
+        }
+        sizes.push_back({(F.ny + 1) / 2, xper ? F.nx / 2 : (F.nx + 1) / 2});
+    }
+    M.lev.resize(sizes.size());
+    for (size_t l = 1; l < sizes.size(); l++) {
+        Level &L = M.lev[l];
+        L.ny = sizes[l].first; L.nx = sizes[l].second;
+        L.pitch = (L.nx + 2 + 1) & ~1;
+        L.n = (size_t)(L.ny + 2) * L.pitch;
+        for (double **p : {&L.x, &L.b, &L.r, &L.cx, &L.cy, &L.dinv, &L.mass, &L.wall}) {
+            F2D_CUDA(cudaMalloc(p, L.n * sizeof(double)));
+            F2D_CUDA(cudaMemsetAsync(*p, 0, L.n * sizeof(double), c->stream));
+        }
+        F2D_CUDA(cudaMalloc(&L.code, L.n));
+        F2D_CUDA(cudaMemsetAsync(L.code, 0, L.n, c->stream));
+    }
+    M.lev[0].ny = F.ny; M.lev[0].nx = F.nx;
+    // coefficients, level by level
+    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0);
+    LAUNCH_CHECK(c);
+    k_build_dinv<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(M.lev[1], xper);
+    LAUNCH_CHECK(c);
+    for (size_t l = 1; l + 1 < M.lev.size(); l++) {
+        Level &Lc = M.lev[l + 1];
+        double pw = std::ldexp(1.0, (int)l);   // 2^l, producing level l+1
+        k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.lev[l], Lc, xper, (pw + 1.0) / (2.0 * pw + 1.0));
+        LAUNCH_CHECK(c);
+        k_build_dinv<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(Lc, xper);
+        LAUNCH_CHECK(c);
+    }
+    // prolongation weights
+    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], xper);
+    LAUNCH_CHECK(c);
+    for (size_t l = 1; l + 1 < M.lev.size(); l++) {
+        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper);
+        LAUNCH_CHECK(c);
+    }
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t l = 1; l < M.lev.size(); l++) {   // set-up only arrays
+        cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
+        cudaFree(M.lev[l].wall); M.lev[l].wall = nullptr;
+    }
+    for (double **p : {&M.r, &M.z, &M.p, &M.q}) {
+        F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
+    }
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    M.built = true;
+    return F2D_OK;
+}
+
+// One V-cycle on the fine problem  L x = fscale*f.  zero_guess: x is taken as
+// 0 on entry (preconditioner use) and never read before it is written.
+static int vcycle(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale, bool zero_guess) {
+    const FineView &F = M.fine;
+    const int xper = F.periodic;
+    const int nu1 = c->cfg.nu1 > 0 ? c->cfg.nu1 : 2, nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
+    const int nlev = (int)M.lev.size();
+    cudaStream_t st = c->stream;
+    dim3 g0 = grd(F.nx, F.ny);
+    // ---- down
+    for (int s = 0; s < nu1; s++)
+        for (int col = 0; col < 2; col++) {
+            if (zero_guess && s == 0 && col == 0) {
+                // x may hold anything: clear the unknowns of the other colour first
+                k_smooth0<true><<<g0, blk(), 0, st>>>(F, x, f, 0.0, 1);
+                LAUNCH_CHECK(c);
+                k_smooth0<true><<<g0, blk(), 0, st>>>(F, x, f, fscale, 0);
+            } else
+                k_smooth0<false><<<g0, blk(), 0, st>>>(F, x, f, fscale, col);
+            LAUNCH_CHECK(c);
+        }
+    // M.q is free while a V-cycle runs (CG only uses it between apply and update)
+    k_resid0<<<g0, blk(), 0, st>>>(F, x, f, fscale, M.q);
+    LAUNCH_CHECK(c);
+    {
+        CoarseView C1 = view_of(M.lev[1], xper, F.dirichlet);
+        k_restrict0<<<grd(C1.nx, C1.ny), blk(), 0, st>>>(F, M.q, C1, M.lev[1].b);
+        LAUNCH_CHECK(c);
+    }
+    for (int l = 1; l < nlev - 1; l++) {
+        Level &L = M.lev[l];
+        CoarseView V = view_of(L, xper, F.dirichlet);
+        dim3 g = grd(L.nx, L.ny);
+        F2D_CUDA(cudaMemsetAsync(L.x, 0, L.n * sizeof(double), st));
+        for (int s = 0; s < nu1; s++)
+            for (int col = 0; col < 2; col++) {
+                if (s == 0 && col == 0) k_smooth<true><<<g, blk(), 0, st>>>(V, L.x, L.b, col);
+                else k_smooth<false><<<g, blk(), 0, st>>>(V, L.x, L.b, col);
+                LAUNCH_CHECK(c);
+            }
+        k_resid<<<g, blk(), 0, st>>>(V, L.x, L.b, L.r);
+        LAUNCH_CHECK(c);
+        CoarseView C = view_of(M.lev[l + 1], xper, F.dirichlet);
+        k_restrict<<<grd(C.nx, C.ny), blk(), 0, st>>>(V, L.r, C, M.lev[l + 1].b);
+        LAUNCH_CHECK(c);
+    }
+    // ---- coarsest
+    {
+        Level &L = M.lev[nlev - 1];
+        int npts = L.ny * L.nx;
+        int nsw = npts <= 64 ? 8 : 24;
+        k_coarsest<<<1, 1024, 0, st>>>(view_of(L, xper, F.dirichlet), L.x, L.b, nsw);
+        LAUNCH_CHECK(c);
+    }
+    // ---- up
+    for (int l = nlev - 2; l >= 1; l--) {
+        Level &L = M.lev[l];
+        CoarseView V = view_of(L, xper, F.dirichlet);
+        dim3 g = grd(L.nx, L.ny);
+        k_prolong<<<g, blk(), 0, st>>>(V, L.x, view_of(M.lev[l + 1], xper, F.dirichlet), M.lev[l + 1].x);
+        LAUNCH_CHECK(c);
+        for (int s = 0; s < nu2; s++)
+            for (int col = 1; col >= 0; col--) {
+                k_smooth<false><<<g, blk(), 0, st>>>(V, L.x, L.b, col);
+                LAUNCH_CHECK(c);
+            }
+    }
+    k_prolong0<<<g0, blk(), 0, st>>>(F, x, view_of(M.lev[1], xper, F.dirichlet), M.lev[1].x);
+    LAUNCH_CHECK(c);
+    for (int s = 0; s < nu2; s++)
+        for (int col = 1; col >= 0; col--) {
+            k_smooth0<false><<<g0, blk(), 0, st>>>(F, x, f, fscale, col);
+            LAUNCH_CHECK(c);
+        }
+    return F2D_OK;
+}
+
+static int read_scalars(f2d_ctx *c, int first, int count) {
+    F2D_CUDA(cudaMemcpyAsync(c->h_scal + first, c->d_scal + first, count * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    return F2D_OK;
+}
+
+int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters_out,
+             double *relres_out) {
+    if (which < 0 || which > 2) { set_error("solver id %d", which); return F2D_ERR_ARG; }
+    Multigrid &M = c->mg[which];
+    if (!M.built) { set_error("solver %d not built (call f2d_set_mask; Helmholtz needs a qg/rsw model)", which); return F2D_ERR_STATE; }
+    if (iters_out) *iters_out = 0;
+    if (relres_out) *relres_out = 0.0;
+    if (M.nunknown == 0) return op_fill(c, x);
+    const FineView &F = M.fine;
+    cudaStream_t st = c->stream;
+    const double rtol = c->cfg.solver_rtol > 0 ? c->cfg.solver_rtol : 1e-12;
+    const int maxit = c->cfg.solver_maxit > 0 ? c->cfg.solver_maxit : 100;
+    const double fscale = -bscale;   // L = -A
+    const int nblk = c->nsm * 8;
+    double *S = c->d_scal;
+    int it = 0;
+    double relres = 0.0;
+    bool conv = false;
+
+    if (c->cfg.solver_kind == 1) {
+        // plain V-cycle iteration
+        for (it = 0; it <= maxit; it++) {
+            k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, nullptr, c->d_part, c->d_count, S + S_RR);
+            LAUNCH_CHECK(c);
+            F2D_TRY(read_scalars(c, S_RR, 2));
+            double rr = c->h_scal[S_RR], ff = c->h_scal[S_FF];
+            relres = ff > 0 ? std::sqrt(rr / ff) : 0.0;
+            if (ff == 0.0) {
+                for (int col = 0; col < 2; col++) {
+                    k_smooth0<true><<<grd(F.nx, F.ny), blk(), 0, st>>>(F, x, b, 0.0, col);
+                    LAUNCH_CHECK(c);
+                }
+                conv = true;
+                break;
+            }
+            if (!(relres > rtol)) { conv = true; break; }
+            if (it == maxit) break;
+            F2D_TRY(vcycle(c, M, x, b, fscale, false));
+        }
+    } else {
+        // preconditioned conjugate gradients, M^-1 = one V-cycle from zero
+        k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
+        LAUNCH_CHECK(c);
+        F2D_TRY(read_scalars(c, S_RR, 2));
+        double ff = c->h_scal[S_FF];
+        relres = ff > 0 ? std::sqrt(c->h_scal[S_RR] / ff) : 0.0;
+        if (ff == 0.0) {   // b == 0: the solution is 0 (up to the Neumann null space)
+            for (int col = 0; col < 2; col++) {
+                k_smooth0<true><<<grd(F.nx, F.ny), blk(), 0, st>>>(F, x, b, 0.0, col);
+                LAUNCH_CHECK(c);
+            }
+            conv = true;
+        } else if (!(relres > rtol)) conv = true;
+        for (it = 0; !conv && it < maxit; it++) {
+            F2D_TRY(vcycle(c, M, M.z, M.r, 1.0, true));
+            k_dot<<<nblk, 256, 0, st>>>(F, M.r, M.z, c->d_part, c->d_count, S + (it == 0 ? S_RZ : S_RZNEW));
+            LAUNCH_CHECK(c);
+            k_cg_dir<<<nblk, 256, 0, st>>>(F, M.p, M.z, S, it == 0);
+            LAUNCH_CHECK(c);
+            if (it > 0) { k_cg_shift<<<1, 1, 0, st>>>(S); LAUNCH_CHECK(c); }
+            k_cg_apply<<<nblk, 256, 0, st>>>(F, M.p, M.q, c->d_part, c->d_count, S + S_PQ);
+            LAUNCH_CHECK(c);
+            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, M.p, M.q, S, c->d_part, c->d_count, S + S_RR);
+            LAUNCH_CHECK(c);
+            F2D_TRY(read_scalars(c, S_RR, 1));
+            relres = std::sqrt(c->h_scal[S_RR] / ff);
+            if (!(relres > rtol)) { conv = true; it++; break; }
+        }
+    }
+    c->nsolves++;
+    c->niters += it;
+    c->max_relres = std::max(c->max_relres, relres);
+    if (iters_out) *iters_out = it;
+    if (relres_out) *relres_out = relres;
+    F2D_TRY(op_fill(c, x));
+    if (!conv || !std::isfinite(relres)) {
+        set_error("elliptic solve %d: relative residual %.3e after %d iterations (rtol %.1e)", which,
+                  relres, it, rtol);
+        return F2D_ERR_NOTCONV;
+    }
+    return F2D_OK;
+}
+
+int mg_apply(f2d_ctx *c, int which, const double *x, double *y) {
+    if (which < 0 || which > 2) { set_error("solver id %d", which); return F2D_ERR_ARG; }
+    Multigrid &M = c->mg[which];
+    if (!M.built) { set_error("solver %d not built", which); return F2D_ERR_STATE; }
+    F2D_CUDA(cudaMemsetAsync(y, 0, c->n * sizeof(double), c->stream));
+    if (M.nunknown == 0) return F2D_OK;
+    k_apply_A<<<grd(M.fine.nx, M.fine.ny), blk(), 0, c->stream>>>(M.fine, x, y);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+// bench.py hook (see bench_step_kernel): fine-level multigrid / CG kernels of
+// the cell-centre solver, timed alone.  Operates on the CG work vectors only.
+int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes) {
+    Multigrid &M = c->mg[F2D_SOLVER_CENTERS];
+    if (!M.built || M.nunknown == 0) { set_error("solver not built"); return F2D_ERR_STATE; }
+    const FineView &F = M.fine;
+    std::string k(name);
+    double npts = (double)F.ny * F.nx;
+    dim3 g0 = grd(F.nx, F.ny);
+    const int nblk = c->nsm * 8;
+    for (int pass = 0; pass < 2; pass++) {
+        int n = pass == 0 ? 2 : reps;
+        if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int r = 0; r < n; r++) {
+            if (k == "mg.smooth_halfsweep") {
+                // one colour: R x(other colour) f(own) W x(own), 1 mask byte per updated point
+                k_smooth0<false><<<g0, blk(), 0, c->stream>>>(F, M.z, M.r, 1.0, r & 1);
+                *bytes = npts * (1.5 * 8 + 0.5);
+            } else if (k == "mg.residual") {
+                k_resid0<<<g0, blk(), 0, c->stream>>>(F, M.z, M.r, 1.0, M.q);
+                *bytes = npts * (3 * 8 + 1);
+            } else if (k == "mg.restrict") {
+                CoarseView C1 = view_of(M.lev[1], F.periodic, F.dirichlet);
+                k_restrict0<<<grd(C1.nx, C1.ny), blk(), 0, c->stream>>>(F, M.q, C1, M.lev[1].b);
+                *bytes = npts * (8 + 1 + 2.0 + 0.25);
+            } else if (k == "mg.prolong") {
+                k_prolong0<<<g0, blk(), 0, c->stream>>>(F, M.z, view_of(M.lev[1], F.periodic, F.dirichlet), M.lev[1].x);
+                *bytes = npts * (2 * 8 + 1 + 2.0);
+            } else if (k == "cg.apply_dot") {
+                k_cg_apply<<<nblk, 256, 0, c->stream>>>(F, M.p, M.q, c->d_part, c->d_count, c->d_scal + S_TMP);
+                *bytes = npts * (2 * 8 + 1);
+            } else if (k == "cg.update") {
+                k_cg_update<<<nblk, 256, 0, c->stream>>>(F, M.z, M.r, M.p, M.q, c->d_scal + 16, c->d_part, c->d_count, c->d_scal + S_TMP);
+                *bytes = npts * (6 * 8 + 1);
+            } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
+            LAUNCH_CHECK(c);
+        }
+    }
+    F2D_CUDA(cudaEventRecord(c->ev1, c->stream));
+    F2D_CUDA(cudaEventSynchronize(c->ev1));
+    F2D_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    *ms /= reps;
+    return F2D_OK;
+}
+
+}  // namespace f2d

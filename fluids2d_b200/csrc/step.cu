@@ -1,0 +1,565 @@
+// Model right-hand sides, Runge-Kutta updates and diagnostics on the device.
+//
+// Each kernel fuses a run of the reference's whole-array numpy passes
+// (operators.py / equations.py / integrators.py) into one sweep; the
+// x-periodic halo copy `mesh.fill` (meshes.py:135-143) is folded in by
+// evaluating halo columns at their periodic image column.  Index arithmetic
+// is the reference's flat-index arithmetic (weno.py:346-405), guarded by the
+// same stencil-order arrays, so interior results depend on the same operands.
+#include "engine.cuh"
+#include "reduce.cuh"
+#include "weno.cuh"
+
+namespace f2d {
+
+struct Grid {
+    int n2, n1, nh, nx, xper;
+    double idx2, idy2;   // 1/dx**2, 1/dy**2   (operators.py:59-64)
+};
+
+static Grid grid_of(const f2d_ctx *c) {
+    Grid g;
+    g.n2 = c->n2; g.n1 = c->n1; g.nh = c->nh; g.nx = c->cfg.nx; g.xper = c->cfg.xperiodic;
+    g.idx2 = c->idx2; g.idy2 = c->idy2;
+    return g;
+}
+
+// column at which a (possibly halo) column is evaluated: its periodic image
+__device__ __forceinline__ int image_col(const Grid &g, int i) {
+    if (g.xper) {
+        if (i < g.nh) return i + g.nx;
+        if (i >= g.n1 - g.nh) return i - g.nx;
+    }
+    return i;
+}
+
+#define THREAD_2D(g)                                         \
+    int i_out = blockIdx.x * blockDim.x + threadIdx.x;       \
+    int j = blockIdx.y * blockDim.y + threadIdx.y;           \
+    if (i_out >= (g).n1 || j >= (g).n2) return;              \
+    int i = image_col((g), i_out);                           \
+    long k = (long)j * (g).n1 + i;                           \
+    long k_out = (long)j * (g).n1 + i_out;                   \
+    const long s1 = (g).n1;                                  \
+    (void)k_out; (void)s1;
+
+static dim3 blk2d() { return dim3(64, 4); }
+static dim3 grd2d(const f2d_ctx *c) { return dim3((c->n1 + 63) / 64, (c->n2 + 3) / 4); }
+
+enum { M_EULER = 0, M_BOUSS = 1, M_RSW = 2, M_QGRSW = 3 };
+
+// ---------------------------------------------------------------------------
+// momentum tendency:  addvortexforce (operators.py:6-13, weno.py:367-385)
+//   + addcoriolis (:32-39) + addgrad(ke) / addgrad(p) (:49-53) + addbuoyancy
+//   (:152-153), then fill.          equations.py:11-15, 29-35, 121-127, 141-148
+// ---------------------------------------------------------------------------
+template <int MV, int MODEL>
+__global__ void __launch_bounds__(256)
+k_rhs_mom(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
+          const double *__restrict__ omega, const double *__restrict__ ke,
+          const double *__restrict__ p, const double *__restrict__ b,
+          const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy,
+          const int8_t *__restrict__ mskx, const int8_t *__restrict__ msky,
+          double fcor, double halfdy, double *__restrict__ dux, double *__restrict__ duy) {
+    THREAD_2D(g);
+    double rx = 0, ry = 0;
+    int oy = ovy[k];
+    if (oy > 0) {   // du.x: V = U.y, s = yshift, s2 = xshift, sign +1
+        double Vm = 0.25 * (((uy[k] * g.idy2 + uy[k + s1] * g.idy2) + uy[k - 1] * g.idy2) +
+                            uy[k + s1 - 1] * g.idy2);
+        double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = omega[k], w3 = omega[k + s1];
+        if (oy > 2) { w1 = omega[k - s1]; w4 = omega[k + 2 * s1]; }
+        if (oy > 4) { w0 = omega[k - 2 * s1]; w5 = omega[k + 3 * s1]; }
+        rx = recon<MV>(oy, Vm, w0, w1, w2, w3, w4, w5) * Vm;
+    }
+    int ox = ovx[k];
+    if (ox > 0) {   // du.y: V = U.x, s = xshift, s2 = yshift, sign -1
+        double Vm = 0.25 * (((ux[k] * g.idx2 + ux[k + 1] * g.idx2) + ux[k - s1] * g.idx2) +
+                            ux[k + 1 - s1] * g.idx2);
+        double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = omega[k], w3 = omega[k + 1];
+        if (ox > 2) { w1 = omega[k - 1]; w4 = omega[k + 2]; }
+        if (ox > 4) { w0 = omega[k - 2]; w5 = omega[k + 3]; }
+        ry = (-recon<MV>(ox, Vm, w0, w1, w2, w3, w4, w5)) * Vm;
+    }
+    if (MODEL == M_RSW || MODEL == M_QGRSW) {   // Coriolis, not masked in the reference
+        if (j <= g.n2 - 2 && i >= 1 && i <= g.n1 - 2)
+            rx += fcor * (((uy[k - 1] * g.idy2 + uy[k + s1 - 1] * g.idy2) + uy[k] * g.idy2) +
+                          uy[k + s1] * g.idy2);
+        if (j >= 1 && j <= g.n2 - 2 && i <= g.n1 - 2)
+            ry -= fcor * (((ux[k - s1] * g.idx2 + ux[k - s1 + 1] * g.idx2) + ux[k] * g.idx2) +
+                          ux[k + 1] * g.idx2);
+    }
+    if (MODEL != M_QGRSW) {
+        if (i >= 1) rx -= (ke[k] - ke[k - 1]) * (double)mskx[k];
+        if (j >= 1) ry -= (ke[k] - ke[k - s1]) * (double)msky[k];
+    }
+    if (MODEL == M_RSW) {
+        if (i >= 1) rx -= (p[k] - p[k - 1]) * (double)mskx[k];
+        if (j >= 1) ry -= (p[k] - p[k - s1]) * (double)msky[k];
+    }
+    if (MODEL == M_BOUSS) {
+        if (j >= 1) ry += (halfdy * (b[k] + b[k - s1])) * (double)msky[k];
+    }
+    dux[k_out] = rx;
+    duy[k_out] = ry;
+}
+
+// ---------------------------------------------------------------------------
+// divflux (operators.py:21-29): face fluxes (weno.py:346-364) ...
+// ---------------------------------------------------------------------------
+template <int MC>
+__global__ void __launch_bounds__(256)
+k_flux(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
+       const double *__restrict__ q, const int8_t *__restrict__ ocx,
+       const int8_t *__restrict__ ocy, double *__restrict__ fx, double *__restrict__ fy) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.n1 || j >= g.n2) return;
+    long k = (long)j * g.n1 + i;
+    const long s1 = g.n1;
+    double rx = 0, ry = 0;
+    int ox = ocx[k];
+    if (ox > 0) {
+        double U = ux[k] * g.idx2;
+        double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = q[k - 1], w3 = q[k];
+        if (ox > 2) { w1 = q[k - 2]; w4 = q[k + 1]; }
+        if (ox > 4) { w0 = q[k - 3]; w5 = q[k + 2]; }
+        rx = recon<MC>(ox, U, w0, w1, w2, w3, w4, w5) * U;
+    }
+    int oy = ocy[k];
+    if (oy > 0) {
+        double U = uy[k] * g.idy2;
+        double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = q[k - s1], w3 = q[k];
+        if (oy > 2) { w1 = q[k - 2 * s1]; w4 = q[k + s1]; }
+        if (oy > 4) { w0 = q[k - 3 * s1]; w5 = q[k + 2 * s1]; }
+        ry = recon<MC>(oy, U, w0, w1, w2, w3, w4, w5) * U;
+    }
+    fx[k] = rx;
+    fy[k] = ry;
+}
+
+// ... and their divergence `div` (operators.py:104-107), then fill.
+__global__ void __launch_bounds__(256)
+k_divflux(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
+          const int8_t *__restrict__ msk, double *__restrict__ dq) {
+    THREAD_2D(g);
+    double d = 0;
+    if (i <= g.n1 - 2) d = -(fx[k + 1] - fx[k]);
+    if (j <= g.n2 - 2) d -= fy[k + s1] - fy[k];
+    dq[k_out] = d * (double)msk[k];
+}
+
+// ---------------------------------------------------------------------------
+// addto_list (integrators.py:154-174): y += ((0 + c0 x0) + c1 x1) + c2 x2
+// ---------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_addto(long n, double *__restrict__ y, const double *__restrict__ x0,
+        const double *__restrict__ x1, const double *__restrict__ x2, double c0, double c1,
+        double c2) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double acc = c0 * x0[k];
+    if (NC > 1) acc = acc + c1 * x1[k];
+    if (NC > 2) acc = acc + c2 * x2[k];
+    y[k] += acc;
+}
+
+// ---------------------------------------------------------------------------
+// pressure_projection, first half (operators.py:114-116): delta = div(sharp(u))
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_div_u(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
+        const int8_t *__restrict__ msk, double *__restrict__ delta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.n1 || j >= g.n2) return;
+    long k = (long)j * g.n1 + i;
+    double d = 0;
+    if (i <= g.n1 - 2) d = -(ux[k + 1] * g.idx2 - ux[k] * g.idx2);
+    if (j <= g.n2 - 2) d -= uy[k + g.n1] * g.idy2 - uy[k] * g.idy2;
+    delta[k] = d * (double)msk[k];
+}
+
+// ---------------------------------------------------------------------------
+// diag:  [addgrad(p, u); fill(u)]  sharp; compute_vorticity (operators.py:67-77);
+//        compute_kinetic_energy (:80-93, weno.py:388-405); [compute_pressure
+//        (:110-111)]; fill(omega, ke).    equations.py:17-22, 37-43, 129-134,
+//        150-155.   `uxin/uyin` hold the un-projected velocity when PROJECT.
+//        MK: innerproduct method (4 = "classic"), -1 = no kinetic energy.
+// ---------------------------------------------------------------------------
+template <int MK, bool PROJECT, int MODEL>
+__global__ void __launch_bounds__(256)
+k_diag(Grid g, const double *__restrict__ uxin, const double *__restrict__ uyin,
+       const double *__restrict__ p, const double *__restrict__ h, const double *__restrict__ hb,
+       const int8_t *__restrict__ msk, const int8_t *__restrict__ mskx,
+       const int8_t *__restrict__ msky, const int8_t *__restrict__ slip,
+       const int8_t *__restrict__ okx, const int8_t *__restrict__ oky, double g_over_area,
+       double *__restrict__ uxo, double *__restrict__ uyo, double *__restrict__ Ux,
+       double *__restrict__ Uy, double *__restrict__ omega, double *__restrict__ ke,
+       double *__restrict__ pout) {
+    THREAD_2D(g);
+    // velocity after the projection, at flat offset m from k (column i + di)
+    auto UX = [&](long m, int di) -> double {
+        double v = uxin[k + m];
+        if (PROJECT && (i + di) >= 1) v -= (p[k + m] - p[k + m - 1]) * (double)mskx[k + m];
+        return v;
+    };
+    auto UY = [&](long m, int dj) -> double {
+        double v = uyin[k + m];
+        if (PROJECT && (j + dj) >= 1) v -= (p[k + m] - p[k + m - s1]) * (double)msky[k + m];
+        return v;
+    };
+    double ux0 = UX(0, 0), uy0 = UY(0, 0);
+    if (PROJECT) { uxo[k_out] = ux0; uyo[k_out] = uy0; }
+    Ux[k_out] = ux0 * g.idx2;
+    Uy[k_out] = uy0 * g.idy2;
+    double om = 0;
+    if (j >= 1) om = -(ux0 - UX(-s1, 0));
+    if (i >= 1) om += uy0 - UY(-1, 0);
+    omega[k_out] = om * (double)slip[k];
+    if (MK >= 0) {
+        double e = 0;
+        if (MK == F2D_METHOD_CLASSIC) {   // operators.py:86-89
+            if (i <= g.n1 - 2) {
+                double a = UX(1, 1);
+                e = a * (a * g.idx2) + ux0 * (ux0 * g.idx2);
+            }
+            if (j <= g.n2 - 2) {
+                double a = UY(s1, 1);
+                e += a * (a * g.idy2) + uy0 * (uy0 * g.idy2);
+            }
+            e *= (double)msk[k] * 0.25;
+        } else {
+            constexpr int M = MK < 0 ? 0 : (MK > 3 ? 0 : MK);
+            int ox = okx[k];
+            if (ox > 0) {
+                double w3 = UX(1, 1);
+                double Um = 0.5 * (ux0 * g.idx2 + w3 * g.idx2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (ox > 2) { w1 = UX(-1, -1); w4 = UX(2, 2); }
+                if (ox > 4) { w0 = UX(-2, -2); w5 = UX(3, 3); }
+                e += recon<M>(ox, Um, w0, w1, ux0, w3, w4, w5) * Um;
+            }
+            int oy = oky[k];
+            if (oy > 0) {
+                double w3 = UY(s1, 1);
+                double Um = 0.5 * (uy0 * g.idy2 + w3 * g.idy2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (oy > 2) { w1 = UY(-s1, -1); w4 = UY(2 * s1, 2); }
+                if (oy > 4) { w0 = UY(-2 * s1, -2); w5 = UY(3 * s1, 3); }
+                e += recon<M>(oy, Um, w0, w1, uy0, w3, w4, w5) * Um;
+            }
+            e *= (double)msk[k] * 0.5;
+        }
+        ke[k_out] = e;
+    }
+    if (MODEL == M_RSW) pout[k_out] = g_over_area * (h[k] + hb[k]);
+}
+
+// ---------------------------------------------------------------------------
+// qg_projection of the tendency (operators.py:176-211), anomaly form
+// ---------------------------------------------------------------------------
+// pv = curl(du) * slip ; pv[1:,1:] += 1/4 sum4(dh * (-f0/H)) ; pv *= mskv
+__global__ void __launch_bounds__(256)
+k_qg_pv(Grid g, const double *__restrict__ dux, const double *__restrict__ duy,
+        const double *__restrict__ dh, const int8_t *__restrict__ slip,
+        const int8_t *__restrict__ mskv, double mf0H, double *__restrict__ pv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.n1 || j >= g.n2) return;
+    long k = (long)j * g.n1 + i;
+    const long s1 = g.n1;
+    double om = 0;
+    if (j >= 1) om = -(dux[k] - dux[k - s1]);
+    if (i >= 1) om += duy[k] - duy[k - 1];
+    om *= (double)slip[k];
+    if (i >= 1 && j >= 1)
+        om += 0.25 * (((dh[k - s1 - 1] * mf0H + dh[k - 1] * mf0H) + dh[k - s1] * mf0H) + dh[k] * mf0H);
+    pv[k] = om * (double)mskv[k];
+}
+
+// dh = verticestocenters(psi * (f0*area/g)) * msk * msk ; du = perpgrad(psi) ; fill
+__global__ void __launch_bounds__(256)
+k_qg_back(Grid g, const double *__restrict__ psi, const int8_t *__restrict__ msk,
+          const int8_t *__restrict__ mskx, const int8_t *__restrict__ msky,
+          const int8_t *__restrict__ mskv, double f0ag, double *__restrict__ dux,
+          double *__restrict__ duy, double *__restrict__ dh) {
+    THREAD_2D(g);
+    if (j <= g.n2 - 2 && i <= g.n1 - 2) {
+        int coef = mskv[k] + mskv[k + s1] + mskv[k + 1] + mskv[k + s1 + 1];
+        double sum = ((psi[k] * f0ag + psi[k + s1] * f0ag) + psi[k + 1] * f0ag) + psi[k + s1 + 1] * f0ag;
+        // the reference yields inf*0 = NaN in cells with no fluid vertex; those
+        // cells are masked, we store 0 there instead.
+        double v = coef > 0 ? (1.0 / (double)coef) * sum : 0.0;
+        double m = (double)msk[k];
+        dh[k_out] = (v * m) * m;
+    } else if (i_out == i) {
+        dh[k_out] = dh[k_out] * (double)msk[k] * (double)msk[k];
+    }
+    if (j <= g.n2 - 2) dux[k_out] = -(psi[k + s1] - psi[k]) * (double)mskx[k];
+    if (i <= g.n1 - 2) duy[k_out] = (psi[k + 1] - psi[k]) * (double)msky[k];
+}
+
+// Model.set_dt (model.py:85): max|U.x|, max|U.y|
+__global__ void __launch_bounds__(256)
+k_maxabs(long n, const double *__restrict__ ux, const double *__restrict__ uy, double idx2,
+         double idy2, double *part, unsigned int *count, double *out) {
+    double v[2] = {0.0, 0.0};
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+        v[0] = fmax(v[0], fabs(ux[k] * idx2));
+        v[1] = fmax(v[1], fabs(uy[k] * idy2));
+    }
+    grid_reduce<OpMax, 2>(v, part, count, out);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+#define LAUNCH_CHECK(c)                 \
+    do {                                \
+        (c)->launches++;                \
+        F2D_CUDA(cudaGetLastError());   \
+    } while (0)
+
+template <int MODEL>
+static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy) {
+    Grid g = grid_of(c);
+    const double *p = c->has("p") ? c->f("p") : nullptr;
+    const double *b = c->has("b") ? c->f("b") : nullptr;
+    const double *ke = c->f("ke");
+    double fcor = c->cfg.f0 * c->area * 0.25;
+    double halfdy = 0.5 * c->dy;
+#define RHS_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), ke, p, b, c->m("ov.x"), c->m("ov.y"), \
+                 c->m("mskx"), c->m("msky"), fcor, halfdy, dux, duy
+    switch (c->cfg.vortexforce) {
+    case F2D_METHOD_WENO: k_rhs_mom<WENO, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_UPWIND: k_rhs_mom<UPWIND, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_CENTERED: k_rhs_mom<CENTERED, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_CWENO: k_rhs_mom<CWENO, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    default: set_error("bad vortexforce method"); return F2D_ERR_ARG;
+    }
+#undef RHS_ARGS
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+static int launch_divflux(f2d_ctx *c, const double *q, double *dq) {
+    Grid g = grid_of(c);
+    double *fx = c->f("flx.x"), *fy = c->f("flx.y");
+#define FLX_ARGS g, c->f("u.x"), c->f("u.y"), q, c->m("oc.x"), c->m("oc.y"), fx, fy
+    switch (c->cfg.compflux) {
+    case F2D_METHOD_WENO: k_flux<WENO><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_UPWIND: k_flux<UPWIND><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_CENTERED: k_flux<CENTERED><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_CWENO: k_flux<CWENO><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    default: set_error("bad compflux method"); return F2D_ERR_ARG;
+    }
+#undef FLX_ARGS
+    LAUNCH_CHECK(c);
+    k_divflux<<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dq);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+static std::string dsname(int k, const char *leaf) { return "ds" + std::to_string(k) + "." + leaf; }
+
+int model_rhs(f2d_ctx *c, int k) {
+    if (!c->mesh_ready) { set_error("f2d_rhs before f2d_set_mask"); return F2D_ERR_STATE; }
+    if (k < 0 || k >= c->nstages) { set_error("stage %d out of range", k); return F2D_ERR_ARG; }
+    double *dux = c->f(dsname(k, "u.x")), *duy = c->f(dsname(k, "u.y"));
+    Grid g = grid_of(c);
+    switch (c->cfg.model) {
+    case F2D_MODEL_EULER:
+        return launch_rhs_mom<M_EULER>(c, dux, duy);
+    case F2D_MODEL_BOUSSINESQ:
+        F2D_TRY(launch_rhs_mom<M_BOUSS>(c, dux, duy));
+        return launch_divflux(c, c->f("b"), c->f(dsname(k, "b")));
+    case F2D_MODEL_RSW:
+        F2D_TRY(launch_rhs_mom<M_RSW>(c, dux, duy));
+        return launch_divflux(c, c->f("h"), c->f(dsname(k, "h")));
+    case F2D_MODEL_QGRSW: {
+        double *dh = c->f(dsname(k, "h"));
+        // un-filled tendencies first (the projection reads them before fill)
+        F2D_TRY(launch_rhs_mom<M_QGRSW>(c, dux, duy));
+        F2D_TRY(launch_divflux(c, c->f("h"), dh));
+        double mf0H = -c->cfg.f0 / c->cfg.H;
+        k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, dux, duy, dh, c->m("slip"), c->m("mskv"),
+                                                      mf0H, c->f("pv"));
+        LAUNCH_CHECK(c);
+        F2D_TRY(mg_solve(c, F2D_SOLVER_HELMHOLTZ, c->f("pv"), 1.0, c->f("psi"), nullptr, nullptr));
+        double f0ag = c->cfg.f0 * c->area / c->cfg.g;
+        k_qg_back<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("msk"), c->m("mskx"),
+                                                        c->m("msky"), c->m("mskv"), f0ag, dux, duy, dh);
+        LAUNCH_CHECK(c);
+        return F2D_OK;
+    }
+    }
+    set_error("unknown model %d", c->cfg.model);
+    return F2D_ERR_ARG;
+}
+
+int model_addto(f2d_ctx *c, int ncoef, const double *coefs) {
+    if (ncoef < 1 || ncoef > 3 || ncoef > c->nstages) { set_error("addto: ncoef=%d", ncoef); return F2D_ERR_ARG; }
+    long n = (long)c->n;
+    unsigned grd = (unsigned)((n + 255) / 256);
+    for (const std::string &leaf : c->prognostic) {
+        double *y = c->f(leaf);
+        const double *x0 = c->f(dsname(0, leaf.c_str()));
+        const double *x1 = ncoef > 1 ? c->f(dsname(1, leaf.c_str())) : nullptr;
+        const double *x2 = ncoef > 2 ? c->f(dsname(2, leaf.c_str())) : nullptr;
+        double c0 = coefs[0], c1 = ncoef > 1 ? coefs[1] : 0, c2 = ncoef > 2 ? coefs[2] : 0;
+        if (ncoef == 1) k_addto<1><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, c0, c1, c2);
+        else if (ncoef == 2) k_addto<2><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, c0, c1, c2);
+        else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, c0, c1, c2);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+
+template <bool PROJECT, int MODEL>
+static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int mk) {
+    Grid g = grid_of(c);
+    const double *p = c->has("p") ? c->f("p") : nullptr;
+    const double *h = c->has("h") ? c->f("h") : nullptr;
+    double goa = c->cfg.g / c->area;
+#define DIAG_ARGS g, uxin, uyin, p, h, c->hb, c->m("msk"), c->m("mskx"), c->m("msky"), c->m("slip"), \
+                  c->m("ok.x"), c->m("ok.y"), goa, c->f("u.x"), c->f("u.y"), c->f("U.x"), c->f("U.y"), \
+                  c->f("omega"), c->f("ke"), c->has("p") ? c->f("p") : nullptr
+    switch (mk) {
+    case -1: k_diag<-1, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    case F2D_METHOD_WENO: k_diag<0, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    case F2D_METHOD_UPWIND: k_diag<1, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    case F2D_METHOD_CENTERED: k_diag<2, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    case F2D_METHOD_CWENO: k_diag<3, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    case F2D_METHOD_CLASSIC: k_diag<4, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
+    default: set_error("bad innerproduct method"); return F2D_ERR_ARG;
+    }
+#undef DIAG_ARGS
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+int model_diag(f2d_ctx *c) {
+    if (!c->mesh_ready) { set_error("f2d_diag before f2d_set_mask"); return F2D_ERR_STATE; }
+    Grid g = grid_of(c);
+    switch (c->cfg.model) {
+    case F2D_MODEL_EULER:
+    case F2D_MODEL_BOUSSINESQ: {
+        double *ux = c->f("u.x"), *uy = c->f("u.y");
+        k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, ux, uy, c->m("msk"), c->f("div"));
+        LAUNCH_CHECK(c);
+        // A p = -delta * area       (operators.py:117)
+        F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
+        // the projection reads neighbours of u, so it cannot run in place:
+        // copy the un-projected velocity aside first
+        size_t bytes = c->n * sizeof(double);
+        F2D_CUDA(cudaMemcpyAsync(c->tmp[0], ux, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        F2D_CUDA(cudaMemcpyAsync(c->tmp[1], uy, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        return launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct);
+    }
+    case F2D_MODEL_RSW:
+        return launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct);
+    case F2D_MODEL_QGRSW:
+        return launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1);
+    }
+    set_error("unknown model %d", c->cfg.model);
+    return F2D_ERR_ARG;
+}
+
+// integrators.py:82-124, incremental form
+static int rk_coefs(int integ, double dt, int stage, double *co) {
+    switch (integ) {
+    case F2D_INT_EF: co[0] = dt; return 1;
+    case F2D_INT_RK3:
+        if (stage == 0) { co[0] = dt; return 1; }
+        if (stage == 1) { co[0] = -3 * dt / 4; co[1] = dt / 4; return 2; }
+        co[0] = -dt / 12; co[1] = -dt / 12; co[2] = 2 * dt / 3; return 3;
+    case F2D_INT_ENRK3:
+        if (stage == 0) { co[0] = dt / 3; return 1; }
+        if (stage == 1) { co[0] = -dt / 3 - 5 * dt / 48; co[1] = 15 * dt / 16; return 2; }
+        co[0] = 5 * dt / 48 + dt / 10; co[1] = -7 * dt / 16; co[2] = 2 * dt / 5; return 3;
+    }
+    return 0;
+}
+
+int model_step(f2d_ctx *c, double dt, int nsteps) {
+    if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
+    for (int it = 0; it < nsteps; it++) {
+        for (int s = 0; s < c->nstages; s++) {
+            double co[3];
+            int nc = rk_coefs(c->cfg.integrator, dt, s, co);
+            F2D_TRY(model_rhs(c, s));
+            F2D_TRY(model_addto(c, nc, co));
+            F2D_TRY(model_diag(c));
+        }
+    }
+    return F2D_OK;
+}
+
+int max_abs_U(f2d_ctx *c, double *out) {
+    int nb = c->nsm * 8;
+    k_maxabs<<<nb, 256, 0, c->stream>>>((long)c->n, c->f("u.x"), c->f("u.y"), c->idx2, c->idy2,
+                                        c->d_part, c->d_count, c->d_scal + 8);
+    LAUNCH_CHECK(c);
+    F2D_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c->h_scal[0] + c->h_scal[1];
+    return F2D_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// bench.py hook: time one kernel alone, `reps` launches between two events on
+// the context's stream.  *bytes = algorithmic bytes of ONE launch (every
+// distinct array read once / written once, fp64 = 8 B, masks = 1 B).
+// Clobbers the scratch tendencies and the diagnostics: call it last.
+// ---------------------------------------------------------------------------
+int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes) {
+    if (!c->mesh_ready) { set_error("bench before f2d_set_mask"); return F2D_ERR_STATE; }
+    if (c->cfg.model != F2D_MODEL_EULER || c->nstages != 3) {
+        set_error("kernel benches are defined for the euler model with a 3-stage integrator");
+        return F2D_ERR_UNSUPPORTED;
+    }
+    std::string k(name);
+    Grid g = grid_of(c);
+    double npts = (double)c->n;
+    if (k == "project_diag") {
+        F2D_CUDA(cudaMemcpyAsync(c->tmp[0], c->f("u.x"), c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        F2D_CUDA(cudaMemcpyAsync(c->tmp[1], c->f("u.y"), c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (int pass = 0; pass < 2; pass++) {   // pass 0 = warm-up
+        int n = pass == 0 ? 2 : reps;
+        if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int r = 0; r < n; r++) {
+            if (k == "advection") {
+                // R u.x u.y omega ke, W ds.x ds.y, masks ov.x ov.y mskx msky
+                F2D_TRY(launch_rhs_mom<M_EULER>(c, c->f("ds0.u.x"), c->f("ds0.u.y")));
+                *bytes = npts * (6 * 8 + 4);
+            } else if (k == "rk_update") {
+                // R u ds0 ds1 ds2, W u (one component; coefficients 0 keep u intact)
+                long n1 = (long)c->n;
+                k_addto<3><<<(unsigned)((n1 + 255) / 256), 256, 0, c->stream>>>(
+                    n1, c->f("u.x"), c->f("ds0.u.x"), c->f("ds1.u.x"), c->f("ds2.u.x"), 0.0, 0.0, 0.0);
+                LAUNCH_CHECK(c);
+                *bytes = npts * (5 * 8);
+            } else if (k == "divergence") {
+                // R u.x u.y, W div, mask msk
+                k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("u.x"), c->f("u.y"), c->m("msk"), c->f("div"));
+                LAUNCH_CHECK(c);
+                *bytes = npts * (3 * 8 + 1);
+            } else if (k == "project_diag") {
+                // R p u.x u.y, W u.x u.y U.x U.y omega ke, masks msk mskx msky slip ok.x ok.y
+                F2D_TRY((launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct)));
+                *bytes = npts * (9 * 8 + 6);
+            } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
+        }
+    }
+    F2D_CUDA(cudaEventRecord(c->ev1, c->stream));
+    F2D_CUDA(cudaEventSynchronize(c->ev1));
+    F2D_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    *ms /= reps;
+    return F2D_OK;
+}
+
+}  // namespace f2d

@@ -1,0 +1,158 @@
+"""Model driver (reference: src/fluids2d/model.py:12-123): same attributes and
+loop, with the state resident on the device between observation points."""
+import signal
+from time import time as _wall
+
+from . import weno as _weno
+from .equations import addforcingterm
+from .integrators import get_integrator
+from .meshes import Mesh
+from .param import DEVICE_MODELS
+from .states import State
+from .timeline import Time
+
+
+class _NoIO:
+    """history output stays on the host application (SURVEY: io.py is out of
+    scope); nhis > 0 needs a writer object with .write(state, time)"""
+
+    def __init__(self, param):
+        if param.nhis > 0:
+            raise NotImplementedError(
+                "NetCDF history stays on the host: set model.io to an object with "
+                "write(state, time) (e.g. the reference's fluids2d.io.IO) or use nhis = 0")
+
+    def write(self, state, time):
+        pass
+
+
+class Model:
+    def __init__(self, param):
+        param.check()
+        if param.model not in DEVICE_MODELS:
+            raise NotImplementedError(
+                f"model '{param.model}' is not on the B200 hot path ({', '.join(DEVICE_MODELS)})")
+        self.param = param
+        self.mesh = Mesh(param)
+        _weno.bind(self.mesh.engine)
+        self.state = State(param, self.mesh.shape)
+        self.set_integrator()
+        self.time = Time(param)
+        self.io = _NoIO(param)
+        self.callbacks = []
+        self.diags = []
+        self.stop = False
+
+    def set_integrator(self):
+        self.integrator = get_integrator(self.param, self.mesh, self.state)
+
+    # ------------------------------------------------------------------ run ---
+    def _observation_due(self):
+        t = self.time
+        return bool(self.diags) or t.update_anim or t.save_to_file or t.finished
+
+    def run(self):
+        if self.param.animation:
+            self.execute_callbacks()
+        self.stop = False
+
+        def handler(sig, frame):
+            print("\n hit ctrl-C, stopping", end="")
+            self.stop = True
+
+        try:
+            signal.signal(signal.SIGINT, handler)
+        except ValueError:
+            pass                      # not in the main thread
+        tic = _wall()
+        self.save_to_file()
+        integ = self.integrator
+        resident = integ.rhs is integ._device_rhs
+        if resident:
+            integ.upload(self.state)
+        while (not self.time.finished) and (not self.stop):
+            if resident:
+                self.set_dt(on_device=True)
+                integ.step_resident(self.time.dt, 1)
+                self.time.pushforward()
+                if self._observation_due():
+                    integ.download(self.state)
+            else:
+                self.set_dt()
+                self.step(1)
+            self.progress()
+            self.animation()
+            self.compute_diags()
+            self.save_to_file()
+        if resident:
+            integ.download(self.state)
+        self.progress()
+        self.print_perf(_wall() - tic)
+        self.finalize()
+
+    def finalize(self):
+        for d in self.diags:
+            if hasattr(d, "finalize"):
+                d.finalize()
+
+    def step(self, nsteps=1):
+        integ = self.integrator
+        if nsteps > 1 and integ.rhs is integ._device_rhs and self.param.dt > 0:
+            integ.upload(self.state)
+            integ.step_resident(self.time.dt, nsteps)
+            integ.download(self.state)
+            for _ in range(nsteps):
+                self.time.pushforward()
+            return
+        for _ in range(nsteps):
+            integ.step(self.state, self.time)
+
+    def set_dt(self, on_device=False):
+        """model.py:71-87"""
+        p = self.param
+        if p.dt > 0:
+            self.time.dt = p.dt
+            return
+        if p.model == "rsw":
+            c = (p.g * p.H) ** 0.5
+            maxU = c / self.mesh.dx + c / self.mesh.dy
+        elif on_device:
+            maxU = self.mesh.engine.max_abs_U() + 1e-99
+        else:
+            import numpy as np
+            U = self.state.U
+            maxU = np.max(np.abs(U.x)) + np.max(np.abs(U.y)) + 1e-99
+        self.time.dt = min(p.cfl / maxU, p.dtmax)
+
+    def print_perf(self, elapsed):
+        print()
+        nite = max(self.time.ite - self.time.ite0, 1)
+        perf = elapsed / (self.mesh.nx * self.mesh.ny * nite)
+        print(f"Elapsed: {elapsed:.2f} s  perf: {perf:.2e} s/dof")
+
+    def progress(self):
+        if (self.time.ite % self.param.nprint == 0) or self.time.finished:
+            print(" ".join([f"\rite={self.time.ite}", self.time.tostring(),
+                            f"dt={self.time.dt:.2g}"]), end="")
+
+    def animation(self):
+        if self.time.update_anim:
+            self.execute_callbacks()
+            fig = getattr(self, "figure", None)
+            if fig is not None:
+                fig.update(self.state, self.time)
+
+    def save_to_file(self):
+        if self.time.save_to_file:
+            self.io.write(self.state, self.time)
+
+    def execute_callbacks(self):
+        for func in self.callbacks:
+            func(self.param, self.mesh, self.state, self.time)
+
+    def compute_diags(self):
+        for d in self.diags:
+            d()
+
+    def add_forcing(self, forcing):
+        self.integrator.rhs = addforcingterm(self.param, self.mesh, self.integrator.rhs, forcing)

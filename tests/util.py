@@ -91,3 +91,40 @@ def field_mask(mesh, name):
     if base in ("omega", "pv", "psi"):
         return mesh.mskv
     return mesh.msk
+
+
+# --------------------------------------------------------------------------
+# CUDA-side drivers
+# --------------------------------------------------------------------------
+_PARAM_DEFAULTS = dict(
+    model="euler", nx=40, ny=40, Lx=1.0, Ly=1.0, xperiodic=False, yperiodic=False,
+    halowidth=3, noslip=None, f0=10.0, beta=0.0, g=1, H=1, dt=0.0, cfl=0.9, dtmax=9e99,
+    integrator="rk3", compflux="weno", vortexforce="weno", innerproduct="weno",
+    maxorder=6, tracer=None)
+
+
+def plain_param(**kw):
+    from types import SimpleNamespace
+    d = dict(_PARAM_DEFAULTS)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def engine_for(g, exact=False, **solver_kw):
+    """Engine loaded with a golden case's mask, topography and initial state."""
+    from fluids2d_b200._cabi import Engine
+    e = Engine(plain_param(**g.param), exact=exact, **solver_kw)
+    e.set_mask(g.msk)
+    if g.hb is not None:
+        e.set_topography(g.hb)
+    for k, v in g.fields("init").items():
+        if k.startswith("flx") and g.param["model"] == "euler":
+            continue
+        e.upload(k, v)
+    return e
+
+
+def mesh_masks(e):
+    from types import SimpleNamespace
+    return SimpleNamespace(msk=e.mesh_array("msk"), mskx=e.mesh_array("mskx"),
+                           msky=e.mesh_array("msky"), mskv=e.mesh_array("mskv"))
