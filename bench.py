@@ -214,8 +214,8 @@ def run_ours(args):
     for name in eng.bench_kernel_names():
         kms, kbytes = eng.bench_kernel(name, 20)
         kernels[name] = {"ms": round(kms, 4), "alg_bytes": kbytes,
-                         "gbs": round(kbytes / (kms * 1e-3) / 1e9, 1),
-                         "frac": round(kbytes / (kms * 1e-3) / 1e9 / peak, 3)}
+                         "gbs": round(kbytes / (kms * 1e-3) / 1e9, 1) if kbytes else None,
+                         "frac": round(kbytes / (kms * 1e-3) / 1e9 / peak, 3) if kbytes else None}
     dom = eng.dominant_kernel()
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,

@@ -346,15 +346,15 @@ class Engine:
         self._chk(self.lib.f2d_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
-    BENCH_KERNELS = ("advection", "rk_update", "divergence", "project_diag", "mg.smooth_halfsweep",
-                     "mg.residual", "mg.restrict", "mg.prolong", "cg.apply_dot", "cg.update")
+    BENCH_KERNELS = ("advection", "rk_update", "divergence", "project_diag", "mg.down0", "mg.up0",
+                     "mg.down1", "mg.up1", "mg.tail", "cg.dir_apply", "cg.update")
 
     def bench_kernel_names(self):
         return list(self.BENCH_KERNELS)
 
     def dominant_kernel(self):
-        """the kernel with the largest share of a step (profiles/): the fine-level smoother"""
-        return "mg.smooth_halfsweep"
+        """the kernel with the largest share of a step (profiles/): the fused fine-level up leg"""
+        return "mg.up0"
 
     def bench_kernel(self, name, reps=20):
         ms, nbytes = C.c_float(), C.c_double()

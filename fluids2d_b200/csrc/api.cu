@@ -1,4 +1,5 @@
 // extern "C" surface of libf2d.so (see include/f2d.h).
+#include <algorithm>
 #include <cstring>
 
 #include "engine.cuh"
@@ -110,7 +111,8 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
         for (int t = 0; t < 2; t++) F2D_CUDA(cudaMalloc(&c->tmp[t], c->n * sizeof(double)));
     F2D_CUDA(cudaMalloc(&c->d_scal, 32 * sizeof(double)));
     F2D_CUDA(cudaMemsetAsync(c->d_scal, 0, 32 * sizeof(double), c->stream));
-    F2D_CUDA(cudaMalloc(&c->d_part, 4 * 8192 * sizeof(double)));
+    c->part_capacity = std::max<size_t>(4 * 8192, 4 * (c->n / (40 * 40) + 1024));
+    F2D_CUDA(cudaMalloc(&c->d_part, c->part_capacity * sizeof(double)));
     F2D_CUDA(cudaMalloc(&c->d_count, sizeof(unsigned int)));
     F2D_CUDA(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned int), c->stream));
     F2D_CUDA(cudaMallocHost(&c->h_scal, 32 * sizeof(double)));

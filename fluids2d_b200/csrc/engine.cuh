@@ -35,6 +35,12 @@ enum : uint8_t {
     NB_PJI = 128   //               (Jn, In)
 };
 
+// element type of the coarse multigrid levels: the coarse-grid correction only
+// has to be accurate to a fraction of the error it removes, so levels l >= 1
+// are stored and relaxed in fp32 (half the traffic and shared memory); the fine
+// level, the residuals and every CG scalar stay fp64.
+typedef float CT;
+
 // Fine level: a window of the reference-layout (n2, n1) arrays.
 struct FineView {
     int ny, nx;        // logical size of the window
@@ -53,17 +59,17 @@ struct CoarseView {
     int ny, nx, pitch;
     int periodic;
     int dirichlet;
-    const double *cx;     // coupling across the west face of (J,I)
-    const double *cy;     // coupling across the south face
-    const double *dinv;   // 1/diagonal, 0 where not an unknown
+    const CT *cx;         // coupling across the west face of (J,I)
+    const CT *cy;         // coupling across the south face
+    const CT *dinv;       // 1/diagonal, 0 where not an unknown
     const uint8_t *code;  // NB_SELF | NB_P* bits
 };
 
 struct Level {
     int ny = 0, nx = 0, pitch = 0;
     size_t n = 0;                       // (ny+2)*pitch
-    double *x = nullptr, *b = nullptr, *r = nullptr;
-    double *cx = nullptr, *cy = nullptr, *dinv = nullptr;
+    CT *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr;
+    CT *cx = nullptr, *cy = nullptr, *dinv = nullptr;
     double *mass = nullptr, *wall = nullptr;   // set-up only
     uint8_t *code = nullptr;
 };
@@ -74,7 +80,8 @@ struct Multigrid {
     FineView fine{};
     uint8_t *nb = nullptr;            // fine bits, (n2,n1)
     std::vector<Level> lev;           // lev[0] unused except sizes; lev[l>=1] coarse
-    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr;   // CG vectors (n2,n1)
+    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr, *z2 = nullptr;   // CG vectors (n2,n1)
+    int tail = 1;                     // first level handled by the single-CTA tail kernel
     int64_t nunknown = 0;
 };
 
@@ -104,6 +111,7 @@ struct f2d_ctx {
     // reductions
     double *d_scal = nullptr;       // device scalars
     double *d_part = nullptr;       // per-block partial sums
+    size_t part_capacity = 0;       // doubles
     unsigned int *d_count = nullptr;
     double *h_scal = nullptr;       // pinned mirror
     // solver statistics

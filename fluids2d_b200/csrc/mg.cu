@@ -22,6 +22,7 @@
 
 #include "engine.cuh"
 #include "reduce.cuh"
+#include "mg_tiles.cuh"
 
 namespace f2d {
 
@@ -32,7 +33,10 @@ namespace f2d {
     } while (0)
 
 // device scalar slots
-enum { S_RR = 0, S_FF = 1, S_RZ = 2, S_PQ = 3, S_RZNEW = 4, S_TMP = 5 };
+// device scalar slots (doubles)
+//   k_cg_resid  -> S_RR, S_SUMR, S_FF      k_cg_update -> S_RR, S_SUMR
+//   up leg / k_dot2 -> S_RZNEW, S_SUMZ     k_cg_dir_apply -> S_PQ, S_RZ0 + (it & 1)
+enum { S_RR = 0, S_SUMR = 1, S_FF = 2, S_RZ0 = 3, S_RZ1 = 4, S_PQ = 5, S_RZNEW = 6, S_SUMZ = 7, S_TMP = 8 };
 
 // ------------------------------------------------------------------ helpers --
 __device__ __forceinline__ bool fine_index(const FineView &F, int j, int i, long &idx) {
@@ -140,7 +144,7 @@ k_resid0(FineView F, const double *__restrict__ x, const double *__restrict__ f,
 
 // b_c = sum over the 4x4 fine cells around the aggregate of wy*wx*r~
 __global__ void __launch_bounds__(256)
-k_restrict0(FineView F, const double *__restrict__ r, CoarseView C, double *__restrict__ bc) {
+k_restrict0(FineView F, const double *__restrict__ r, CoarseView C, CT *__restrict__ bc) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= C.nx || J >= C.ny) return;
@@ -168,7 +172,7 @@ k_restrict0(FineView F, const double *__restrict__ r, CoarseView C, double *__re
 
 // x_f += (9 x00 + 3 xn0 + 3 x0n + xnn) / W16
 __global__ void __launch_bounds__(256)
-k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const double *__restrict__ xc) {
+k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const CT *__restrict__ xc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= F.nx || j >= F.ny) return;
@@ -193,11 +197,11 @@ k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const double *__res
     for (long _t = (long)blockIdx.x * blockDim.x + threadIdx.x; _t < _n0;         \
          _t += (long)gridDim.x * blockDim.x)
 
-// r = f - L x ; rr = r.r ; ff = f.f            (CG start / convergence check)
+// r = f - L x ; rr = r.r ; ff = f.f ; sum = 1.r      (CG start / convergence check)
 __global__ void __launch_bounds__(256)
 k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ f, double fscale,
            double *__restrict__ r, double *part, unsigned int *count, double *out) {
-    double v[2] = {0.0, 0.0};
+    double v[3] = {0.0, 0.0, 0.0};
     FINE_LOOP(F) {
         int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
@@ -209,9 +213,26 @@ k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ 
         double res = ff - (s.diag * x[idx] - fine_offdiag(s, c, x));
         if (r) r[idx] = res;
         v[0] += res * res;
-        v[1] += ff * ff;
+        v[1] += res;
+        v[2] += ff * ff;
     }
-    grid_reduce<OpSum, 2>(v, part, count, out);
+    grid_reduce<OpSum, 3>(v, part, count, out);
+}
+
+// r -= mean(r): the all-Neumann operator is singular (constants); a right-hand
+// side that is not orthogonal to them (e.g. a divergence that is pure rounding
+// noise) has no solution, so CG runs on its projection.  Every later residual
+// stays orthogonal because the columns of L sum to zero.
+__global__ void __launch_bounds__(256)
+k_cg_project(FineView F, double *__restrict__ r, const double *__restrict__ scal, double inv_n) {
+    double mean = scal[S_SUMR] * inv_n;
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        if (!(F.nb[idx] & NB_SELF)) continue;
+        r[idx] -= mean;
+    }
 }
 
 // q = L p ; pq = p.q
@@ -234,14 +255,15 @@ k_cg_apply(FineView F, const double *__restrict__ p, double *__restrict__ q, dou
     grid_reduce<OpSum, 1>(v, part, count, out);
 }
 
-// x += alpha p ; r -= alpha q ; rr = r.r          alpha = rz / pq
+// x += alpha p ; r -= alpha q ; (rr, sum r)          alpha = rz / pq
 __global__ void __launch_bounds__(256)
 k_cg_update(FineView F, double *__restrict__ x, double *__restrict__ r,
             const double *__restrict__ p, const double *__restrict__ q,
-            const double *__restrict__ scal, double *part, unsigned int *count, double *out) {
+            const double *__restrict__ scal, int rz_slot, double *part, unsigned int *count,
+            double *out) {
     double pq = scal[S_PQ];
-    double alpha = pq != 0.0 ? scal[S_RZ] / pq : 0.0;
-    double v[1] = {0.0};
+    double alpha = pq != 0.0 ? scal[rz_slot] / pq : 0.0;
+    double v[2] = {0.0, 0.0};
     FINE_LOOP(F) {
         int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
@@ -251,40 +273,67 @@ k_cg_update(FineView F, double *__restrict__ x, double *__restrict__ r,
         double rv = r[idx] - alpha * q[idx];
         r[idx] = rv;
         v[0] += rv * rv;
+        v[1] += rv;
     }
-    grid_reduce<OpSum, 1>(v, part, count, out);
+    grid_reduce<OpSum, 2>(v, part, count, out);
 }
 
-// out = a.b over the unknowns
+// (sum (r - mean r) z, sum z) over the unknowns   (un-fused path; the fused up
+// leg produces the same two numbers)
 __global__ void __launch_bounds__(256)
-k_dot(FineView F, const double *__restrict__ a, const double *__restrict__ b, double *part,
-      unsigned int *count, double *out) {
+k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
+       const double *__restrict__ scal, int sumr_slot, double inv_n, double *part,
+       unsigned int *count, double *out) {
+    double mr = sumr_slot >= 0 ? scal[sumr_slot] * inv_n : 0.0;
+    double v[2] = {0.0, 0.0};
+    FINE_LOOP(F) {
+        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
+        long idx;
+        if (!fine_index(F, j, i, idx)) continue;
+        if (!(F.nb[idx] & NB_SELF)) continue;
+        v[0] += (r[idx] - mr) * z[idx];
+        v[1] += z[idx];
+    }
+    grid_reduce<OpSum, 2>(v, part, count, out);
+}
+
+// pnew = (z - mean z) + beta pold ;  q = L pnew ;  pq = pnew.q
+//   beta = rz_new / rz_old (0 on the first iteration); rz_new is stored in the
+//   slot of this iteration's parity for k_cg_update and the next direction.
+//   pold / pnew are distinct buffers because q needs pnew at the neighbours.
+//   singular operators: z is projected on the complement of the constants, so
+//   that rounding in the V-cycle cannot feed the null space.
+__global__ void __launch_bounds__(256)
+k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restrict__ pold,
+               double *__restrict__ pnew, double *__restrict__ q, double *__restrict__ scal, int it,
+               int singular, double inv_n, double *part, unsigned int *count) {
+    double rznew = scal[S_RZNEW];
+    double mz = singular ? scal[S_SUMZ] * inv_n : 0.0;
+    double beta = 0.0;
+    if (it > 0) { double rzold = scal[S_RZ0 + ((it - 1) & 1)]; beta = rzold != 0.0 ? rznew / rzold : 0.0; }
     double v[1] = {0.0};
     FINE_LOOP(F) {
         int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
-        if (!(F.nb[idx] & NB_SELF)) continue;
-        v[0] += a[idx] * b[idx];
+        uint8_t c = F.nb[idx];
+        if (!(c & NB_SELF)) continue;
+        Stencil s = fine_stencil(F, i, idx, c);
+        auto P = [&](long k) { return (z[k] - mz) + beta * pold[k]; };
+        double pc = P(idx);
+        double off = 0.0;
+        if (c & NB_W) off += s.cw * P(s.iw);
+        if (c & NB_E) off += s.ce * P(s.ie);
+        if (c & NB_S) off += s.cs * P(s.is);
+        if (c & NB_N) off += s.cn * P(s.in);
+        double qv = s.diag * pc - off;
+        pnew[idx] = pc;
+        q[idx] = qv;
+        v[0] += pc * qv;
     }
-    grid_reduce<OpSum, 1>(v, part, count, out);
+    grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_RZ0 + (it & 1)] = rznew;
 }
-
-// p = z + beta p, beta = rz_new / rz (first: p = z); then rz <- rz_new
-__global__ void __launch_bounds__(256)
-k_cg_dir(FineView F, double *__restrict__ p, const double *__restrict__ z,
-         const double *__restrict__ scal, int first) {
-    double beta = 0.0;
-    if (!first) { double rz = scal[S_RZ]; beta = rz != 0.0 ? scal[S_RZNEW] / rz : 0.0; }
-    FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
-        long idx;
-        if (!fine_index(F, j, i, idx)) continue;
-        if (!(F.nb[idx] & NB_SELF)) continue;
-        p[idx] = first ? z[idx] : z[idx] + beta * p[idx];
-    }
-}
-__global__ void k_cg_shift(double *scal) { scal[S_RZ] = scal[S_RZNEW]; }
 
 // y = A x = -L x on the unknowns, 0 elsewhere inside the window
 __global__ void __launch_bounds__(256)
@@ -303,7 +352,7 @@ k_apply_A(FineView F, const double *__restrict__ x, double *__restrict__ y) {
 // ------------------------------------------------------------ coarse levels --
 template <bool ZERO_GUESS>
 __global__ void __launch_bounds__(256)
-k_smooth(CoarseView V, double *__restrict__ x, const double *__restrict__ b, int color) {
+k_smooth(CoarseView V, CT *__restrict__ x, const CT *__restrict__ b, int color) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= V.nx || J >= V.ny || ((I + J) & 1) != color) return;
@@ -317,8 +366,8 @@ k_smooth(CoarseView V, double *__restrict__ x, const double *__restrict__ b, int
 }
 
 __global__ void __launch_bounds__(256)
-k_resid(CoarseView V, const double *__restrict__ x, const double *__restrict__ b,
-        double *__restrict__ r) {
+k_resid(CoarseView V, const CT *__restrict__ x, const CT *__restrict__ b,
+        CT *__restrict__ r) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= V.nx || J >= V.ny) return;
@@ -332,7 +381,7 @@ k_resid(CoarseView V, const double *__restrict__ x, const double *__restrict__ b
 }
 
 __global__ void __launch_bounds__(256)
-k_restrict(CoarseView Vf, const double *__restrict__ r, CoarseView C, double *__restrict__ bc) {
+k_restrict(CoarseView Vf, const CT *__restrict__ r, CoarseView C, CT *__restrict__ bc) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= C.nx || J >= C.ny) return;
@@ -357,7 +406,7 @@ k_restrict(CoarseView Vf, const double *__restrict__ r, CoarseView C, double *__
 }
 
 __global__ void __launch_bounds__(256)
-k_prolong(CoarseView Vf, double *__restrict__ x, CoarseView C, const double *__restrict__ xc) {
+k_prolong(CoarseView Vf, CT *__restrict__ x, CoarseView C, const CT *__restrict__ xc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= Vf.nx || j >= Vf.ny) return;
@@ -377,7 +426,7 @@ k_prolong(CoarseView Vf, double *__restrict__ x, CoarseView C, const double *__r
 
 // coarsest level: nsw sweeps (R,B) then nsw sweeps (B,R) from a zero guess, one CTA
 __global__ void __launch_bounds__(1024)
-k_coarsest(CoarseView V, double *__restrict__ x, const double *__restrict__ b, int nsw) {
+k_coarsest(CoarseView V, CT *__restrict__ x, const CT *__restrict__ b, int nsw) {
     int npts = V.ny * V.nx;
     for (int t = threadIdx.x; t < npts; t += blockDim.x) {
         int J = t / V.nx, I = t - J * V.nx;
@@ -568,9 +617,11 @@ static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
 void mg_free(f2d_ctx *c, int which) {
     Multigrid &M = c->mg[which];
     cudaFree(M.nb);
-    for (double *p : {M.r, M.z, M.p, M.q}) cudaFree(p);
+    for (double *p : {M.r, M.z, M.p, M.q, M.p2, M.z2}) cudaFree(p);
     for (Level &L : M.lev) {
-        for (double *p : {L.x, L.b, L.r, L.cx, L.cy, L.dinv, L.mass, L.wall}) cudaFree(p);
+        for (CT *p : {L.x, L.x2, L.b, L.r, L.cx, L.cy, L.dinv}) cudaFree(p);
+        cudaFree(L.mass);
+        cudaFree(L.wall);
         cudaFree(L.code);
     }
     M = Multigrid();
@@ -657,7 +708,11 @@ int mg_build(f2d_ctx *c, int which) {
         L.ny = sizes[l].first; L.nx = sizes[l].second;
         L.pitch = (L.nx + 2 + 1) & ~1;
         L.n = (size_t)(L.ny + 2) * L.pitch;
-        for (double **p : {&L.x, &L.b, &L.r, &L.cx, &L.cy, &L.dinv, &L.mass, &L.wall}) {
+        for (CT **p : {&L.x, &L.x2, &L.b, &L.r, &L.cx, &L.cy, &L.dinv}) {
+            F2D_CUDA(cudaMalloc(p, L.n * sizeof(CT)));
+            F2D_CUDA(cudaMemsetAsync(*p, 0, L.n * sizeof(CT), c->stream));
+        }
+        for (double **p : {&L.mass, &L.wall}) {
             F2D_CUDA(cudaMalloc(p, L.n * sizeof(double)));
             F2D_CUDA(cudaMemsetAsync(*p, 0, L.n * sizeof(double), c->stream));
         }
@@ -665,6 +720,10 @@ int mg_build(f2d_ctx *c, int which) {
         F2D_CUDA(cudaMemsetAsync(L.code, 0, L.n, c->stream));
     }
     M.lev[0].ny = F.ny; M.lev[0].nx = F.nx;
+    // levels from M.tail on are small enough for the single-CTA tail kernel
+    M.tail = (int)M.lev.size() - 1;
+    for (int l = (int)M.lev.size() - 1; l >= 1; l--)
+        if ((long)M.lev[l].ny * M.lev[l].nx <= 4096 && (int)M.lev.size() - l <= 16) M.tail = l;
     // coefficients, level by level
     k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0);
     LAUNCH_CHECK(c);
@@ -690,7 +749,7 @@ int mg_build(f2d_ctx *c, int which) {
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
         cudaFree(M.lev[l].wall); M.lev[l].wall = nullptr;
     }
-    for (double **p : {&M.r, &M.z, &M.p, &M.q}) {
+    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2, &M.z2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
     }
@@ -699,20 +758,275 @@ int mg_build(f2d_ctx *c, int which) {
     return F2D_OK;
 }
 
-// One V-cycle on the fine problem  L x = fscale*f.  zero_guess: x is taken as
-// 0 on entry (preconditioner use) and never read before it is written.
-static int vcycle(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale, bool zero_guess) {
+// ---------------------------------------------------------------------------
+// single-CTA tail: the whole sub-V-cycle of the levels whose grids are small
+// (<= 4096 points) in one launch, arrays in global memory (L1/L2 resident).
+// ---------------------------------------------------------------------------
+struct TailLevel {
+    int ny, nx, pitch;
+    CT *x, *b, *r;
+    const CT *cx, *cy, *dinv;
+    const uint8_t *code;
+};
+struct TailArgs {
+    int nlev, periodic, dirichlet, nu1, nu2, nsw;
+    TailLevel lev[16];
+};
+
+__device__ __forceinline__ void tail_relax(const TailLevel &L, int periodic, int color, bool zero) {
+    int npts = L.ny * L.nx;
+    for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+        int J = t / L.nx, I = t - J * L.nx;
+        if (((I + J) & 1) != color) continue;
+        long c = (long)(J + 1) * L.pitch + I + 1, w = c - 1, e = c + 1;
+        if (periodic) { if (I == 0) w = c + (L.nx - 1); if (I == L.nx - 1) e = c - (L.nx - 1); }
+        CT di = L.dinv[c];
+        if (di == CT(0)) continue;
+        CT a = CT(0);
+        if (!zero) a = L.cx[c] * L.x[w] + L.cx[e] * L.x[e] + L.cy[c] * L.x[c - L.pitch] + L.cy[c + L.pitch] * L.x[c + L.pitch];
+        L.x[c] = (L.b[c] + a) * di;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_mg_tail(TailArgs A) {
+    const int per = A.periodic;
+    for (int l = 0; l < A.nlev - 1; l++) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        int npts = L.ny * L.nx;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int J = t / L.nx, I = t - J * L.nx;
+            L.x[(long)(J + 1) * L.pitch + I + 1] = CT(0);
+        }
+        __syncthreads();
+        for (int s = 0; s < A.nu1; s++) {
+            tail_relax(L, per, 0, s == 0);
+            tail_relax(L, per, 1, false);
+        }
+        // residual / W16
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int J = t / L.nx, I = t - J * L.nx;
+            long c = (long)(J + 1) * L.pitch + I + 1, w = c - 1, e = c + 1;
+            if (per) { if (I == 0) w = c + (L.nx - 1); if (I == L.nx - 1) e = c - (L.nx - 1); }
+            CT di = L.dinv[c], res = CT(0);
+            if (di != CT(0)) {
+                CT a = L.cx[c] * L.x[w] + L.cx[e] * L.x[e] + L.cy[c] * L.x[c - L.pitch] + L.cy[c + L.pitch] * L.x[c + L.pitch];
+                res = (L.b[c] - (L.x[c] / di - a)) / (CT)w16_of(L.code[c], A.dirichlet);
+            }
+            L.r[c] = res;
+        }
+        __syncthreads();
+        // restriction
+        int nc = C.ny * C.nx;
+        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
+            int J = t / C.nx, I = t - J * C.nx;
+            CT acc = CT(0);
+            for (int a = -1; a <= 2; a++) {
+                int j = 2 * J + a;
+                if (j < 0 || j >= L.ny) continue;
+                CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
+                for (int b = -1; b <= 2; b++) {
+                    int i = 2 * I + b;
+                    if (per) i = wrap_mod(i, L.nx);
+                    else if (i < 0 || i >= L.nx) continue;
+                    CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
+                    acc += wy * wx * L.r[(long)(j + 1) * L.pitch + i + 1];
+                }
+            }
+            C.b[(long)(J + 1) * C.pitch + I + 1] = acc;
+        }
+        __syncthreads();
+    }
+    {   // coarsest: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
+        const TailLevel &L = A.lev[A.nlev - 1];
+        int npts = L.ny * L.nx;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int J = t / L.nx, I = t - J * L.nx;
+            L.x[(long)(J + 1) * L.pitch + I + 1] = CT(0);
+        }
+        __syncthreads();
+        for (int s = 0; s < 4 * A.nsw; s++)
+            tail_relax(L, per, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
+    }
+    for (int l = A.nlev - 2; l >= 0; l--) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        int npts = L.ny * L.nx;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int j = t / L.nx, i = t - j * L.nx;
+            long idx = (long)(j + 1) * L.pitch + i + 1;
+            uint8_t c = L.code[idx];
+            if (!(c & NB_SELF)) continue;
+            int J0, Jn, I0, In;
+            parents(j, i, J0, Jn, I0, In);
+            if (per) In = wrap_mod(In, C.nx);
+            long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;
+            CT v = CT(9) * C.x[r0 + I0 + 1];
+            if (c & NB_PJ) v += CT(3) * C.x[rn + I0 + 1];
+            if (c & NB_PI) v += CT(3) * C.x[r0 + In + 1];
+            if (c & NB_PJI) v += C.x[rn + In + 1];
+            L.x[idx] += v / (CT)w16_of(c, A.dirichlet);
+        }
+        __syncthreads();
+        for (int s = 0; s < A.nu2; s++) {
+            tail_relax(L, per, 1, false);
+            tail_relax(L, per, 0, false);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side of the fused V-cycle
+// ---------------------------------------------------------------------------
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    F2D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return F2D_OK;
+}
+
+static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet) {
+    CoarseArrays<CT> A;
+    A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.dirichlet = dirichlet;
+    A.cx = L.cx; A.cy = L.cy; A.dinv = L.dinv; A.code = L.code;
+    return A;
+}
+
+// where the finished correction of coarse level l lives: the tail kernel works
+// in place, the tile kernels write their up leg to the second buffer
+static const CT *level_result(const Multigrid &M, int l) { return l >= M.tail ? M.lev[l].x : M.lev[l].x2; }
+
+template <int NU, bool ZERO>
+static int launch_down0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout, const double *f, double fscale, int sumr_slot) {
+    constexpr int WJ = 64, H = halo_down(NU, ZERO), TJ = WJ - 2 * H, TI = TW - 2 * H;
+    const FineView &F = M.fine;
+    FineLevel L{F};
+    auto kern = k_mg_down<double, CT, true, ZERO, NU, WJ, FineLevel>;
+    size_t smem = Window<double, true, WJ>::bytes();
+    static bool once = false;
+    if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
+    dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
+    const Level &C = M.lev[1];
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / (double)M.nunknown,
+                                               C.ny, C.nx, C.pitch, C.b);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+template <int NU, bool DOT>
+static int launch_up0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout, const double *f, double fscale, int sumr_slot) {
+    constexpr int WJ = 64, H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
+    const FineView &F = M.fine;
+    FineLevel L{F};
+    auto kern = k_mg_up<double, CT, true, DOT, NU, WJ, FineLevel>;
+    size_t smem = ((Window<double, true, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(double);
+    static bool once = false;
+    if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
+    dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
+    if (DOT && (size_t)g.x * g.y * 2 > c->part_capacity) { set_error("reduction scratch too small"); return F2D_ERR_STATE; }
+    const Level &C = M.lev[1];
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / (double)M.nunknown,
+                                               C.ny, C.nx, C.pitch, F.periodic, level_result(M, 1), c->d_part, c->d_count,
+                                               c->d_scal + S_RZNEW);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+template <int NU, int WJ>
+static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
+    constexpr int H = halo_down(NU, true), TJ = WJ - 2 * H, TI = TW - 2 * H;
+    Level &Lv = M.lev[l];
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet)};
+    auto kern = k_mg_down<CT, CT, false, true, NU, WJ, CoarseLevel<CT>>;
+    size_t smem = Window<CT, false, WJ>::bytes();
+    static bool once = false;
+    if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
+    dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
+    const Level &C = M.lev[l + 1];
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x, Lv.b, 1.0, c->d_scal, -1, 0.0, C.ny, C.nx, C.pitch, C.b);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+template <int NU, int WJ>
+static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
+    constexpr int H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
+    Level &Lv = M.lev[l];
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet)};
+    auto kern = k_mg_up<CT, CT, false, false, NU, WJ, CoarseLevel<CT>>;
+    size_t smem = ((Window<CT, false, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
+    static bool once = false;
+    if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
+    dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
+    const Level &C = M.lev[l + 1];
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x2, Lv.b, 1.0, c->d_scal, -1, 0.0, C.ny, C.nx, C.pitch,
+                                               M.fine.periodic, level_result(M, l + 1), nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+template <int NU>
+static int coarse_down(f2d_ctx *c, Multigrid &M, int l) {
+    return M.lev[l].ny >= 1024 ? launch_down<NU, 64>(c, M, l) : launch_down<NU, 32>(c, M, l);
+}
+template <int NU>
+static int coarse_up(f2d_ctx *c, Multigrid &M, int l) {
+    return M.lev[l].ny >= 1024 ? launch_up<NU, 64>(c, M, l) : launch_up<NU, 32>(c, M, l);
+}
+
+#define NU_SWITCH(nu, CALL)                                   \
+    switch (nu) {                                             \
+    case 1: { constexpr int NU = 1; F2D_TRY(CALL); } break;   \
+    case 2: { constexpr int NU = 2; F2D_TRY(CALL); } break;   \
+    default: { constexpr int NU = 3; F2D_TRY(CALL); } break;  \
+    }
+
+static int launch_tail(f2d_ctx *c, Multigrid &M) {
+    TailArgs A;
+    const int nlev = (int)M.lev.size();
+    A.nlev = nlev - M.tail;
+    A.periodic = M.fine.periodic; A.dirichlet = M.fine.dirichlet;
+    A.nu1 = c->cfg.nu1 > 0 ? c->cfg.nu1 : 2;
+    A.nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
+    const Level &last = M.lev[nlev - 1];
+    A.nsw = last.ny * last.nx <= 64 ? 8 : 24;
+    for (int l = M.tail; l < nlev; l++) {
+        const Level &L = M.lev[l];
+        A.lev[l - M.tail] = TailLevel{L.ny, L.nx, L.pitch, L.x, L.b, L.r, L.cx, L.cy, L.dinv, L.code};
+    }
+    k_mg_tail<<<1, 1024, 0, c->stream>>>(A);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+// One fused V-cycle on  L x = fscale*f - mean  (mean taken from scal[sumr_slot]/N
+// when sumr_slot >= 0).  zero_guess: x is only written.  with_dot: the up leg
+// leaves (sum f x, sum x) in S_RZNEW, S_SUMZ.
+static int vcycle_fused(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale,
+                        bool zero_guess, int sumr_slot, bool with_dot, double *xout) {
+    // down leg: zero guess writes M.z; otherwise reads x and writes M.z (out of
+    // place).  up leg: reads M.z, writes xout (M.z2 for CG, x itself otherwise).
+    const int nu1 = std::min(c->cfg.nu1 > 0 ? c->cfg.nu1 : 2, 3), nu2 = std::min(c->cfg.nu2 > 0 ? c->cfg.nu2 : 2, 3);
+    if (zero_guess) { NU_SWITCH(nu1, (launch_down0<NU, true>(c, M, M.z, M.z, f, fscale, sumr_slot))); }
+    else { NU_SWITCH(nu1, (launch_down0<NU, false>(c, M, x, M.z, f, fscale, sumr_slot))); }
+    for (int l = 1; l < M.tail; l++) { NU_SWITCH(nu1, (coarse_down<NU>(c, M, l))); }
+    F2D_TRY(launch_tail(c, M));
+    for (int l = M.tail - 1; l >= 1; l--) { NU_SWITCH(nu2, (coarse_up<NU>(c, M, l))); }
+    if (with_dot) { NU_SWITCH(nu2, (launch_up0<NU, true>(c, M, M.z, xout, f, fscale, sumr_slot))); }
+    else { NU_SWITCH(nu2, (launch_up0<NU, false>(c, M, M.z, xout, f, fscale, sumr_slot))); }
+    return F2D_OK;
+}
+
+// The same V-cycle with one kernel per half-sweep (solver_kind & 2): kept as the
+// cross-check of the tile kernels.
+static int vcycle_unfused(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale, bool zero_guess) {
     const FineView &F = M.fine;
     const int xper = F.periodic;
     const int nu1 = c->cfg.nu1 > 0 ? c->cfg.nu1 : 2, nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
     const int nlev = (int)M.lev.size();
     cudaStream_t st = c->stream;
     dim3 g0 = grd(F.nx, F.ny);
-    // ---- down
     for (int s = 0; s < nu1; s++)
         for (int col = 0; col < 2; col++) {
             if (zero_guess && s == 0 && col == 0) {
-                // x may hold anything: clear the unknowns of the other colour first
                 k_smooth0<true><<<g0, blk(), 0, st>>>(F, x, f, 0.0, 1);
                 LAUNCH_CHECK(c);
                 k_smooth0<true><<<g0, blk(), 0, st>>>(F, x, f, fscale, 0);
@@ -732,7 +1046,7 @@ static int vcycle(f2d_ctx *c, Multigrid &M, double *x, const double *f, double f
         Level &L = M.lev[l];
         CoarseView V = view_of(L, xper, F.dirichlet);
         dim3 g = grd(L.nx, L.ny);
-        F2D_CUDA(cudaMemsetAsync(L.x, 0, L.n * sizeof(double), st));
+        F2D_CUDA(cudaMemsetAsync(L.x, 0, L.n * sizeof(CT), st));
         for (int s = 0; s < nu1; s++)
             for (int col = 0; col < 2; col++) {
                 if (s == 0 && col == 0) k_smooth<true><<<g, blk(), 0, st>>>(V, L.x, L.b, col);
@@ -745,15 +1059,12 @@ static int vcycle(f2d_ctx *c, Multigrid &M, double *x, const double *f, double f
         k_restrict<<<grd(C.nx, C.ny), blk(), 0, st>>>(V, L.r, C, M.lev[l + 1].b);
         LAUNCH_CHECK(c);
     }
-    // ---- coarsest
     {
         Level &L = M.lev[nlev - 1];
         int npts = L.ny * L.nx;
-        int nsw = npts <= 64 ? 8 : 24;
-        k_coarsest<<<1, 1024, 0, st>>>(view_of(L, xper, F.dirichlet), L.x, L.b, nsw);
+        k_coarsest<<<1, 1024, 0, st>>>(view_of(L, xper, F.dirichlet), L.x, L.b, npts <= 64 ? 8 : 24);
         LAUNCH_CHECK(c);
     }
-    // ---- up
     for (int l = nlev - 2; l >= 1; l--) {
         Level &L = M.lev[l];
         CoarseView V = view_of(L, xper, F.dirichlet);
@@ -783,6 +1094,14 @@ static int read_scalars(f2d_ctx *c, int first, int count) {
     return F2D_OK;
 }
 
+static int zero_unknowns(f2d_ctx *c, const FineView &F, double *x) {
+    for (int col = 0; col < 2; col++) {
+        k_smooth0<true><<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, x, x, 0.0, col);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+
 int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters_out,
              double *relres_out) {
     if (which < 0 || which > 2) { set_error("solver id %d", which); return F2D_ERR_ARG; }
@@ -797,59 +1116,65 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const int maxit = c->cfg.solver_maxit > 0 ? c->cfg.solver_maxit : 100;
     const double fscale = -bscale;   // L = -A
     const int nblk = c->nsm * 8;
+    const bool singular = !F.dirichlet && F.shift == 0.0;
+    const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
+    const double N = (double)M.nunknown, inv_n = 1.0 / N;
     double *S = c->d_scal;
     int it = 0;
     double relres = 0.0;
     bool conv = false;
+    auto projected = [&](double rr, double sum) { return singular ? std::max(rr - sum * sum * inv_n, 0.0) : rr; };
 
-    if (c->cfg.solver_kind == 1) {
-        // plain V-cycle iteration
+    if (plain) {
+        // plain V-cycle iteration on x itself
         for (it = 0; it <= maxit; it++) {
             k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, nullptr, c->d_part, c->d_count, S + S_RR);
             LAUNCH_CHECK(c);
-            F2D_TRY(read_scalars(c, S_RR, 2));
-            double rr = c->h_scal[S_RR], ff = c->h_scal[S_FF];
-            relres = ff > 0 ? std::sqrt(rr / ff) : 0.0;
-            if (ff == 0.0) {
-                for (int col = 0; col < 2; col++) {
-                    k_smooth0<true><<<grd(F.nx, F.ny), blk(), 0, st>>>(F, x, b, 0.0, col);
-                    LAUNCH_CHECK(c);
-                }
-                conv = true;
-                break;
-            }
+            F2D_TRY(read_scalars(c, S_RR, 3));
+            double ff = c->h_scal[S_FF];
+            if (ff == 0.0) { F2D_TRY(zero_unknowns(c, F, x)); conv = true; relres = 0.0; break; }
+            relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
             if (!(relres > rtol)) { conv = true; break; }
             if (it == maxit) break;
-            F2D_TRY(vcycle(c, M, x, b, fscale, false));
+            if (unfused) F2D_TRY(vcycle_unfused(c, M, x, b, fscale, false));
+            else F2D_TRY(vcycle_fused(c, M, x, b, fscale, false, -1, false, x));
         }
     } else {
-        // preconditioned conjugate gradients, M^-1 = one V-cycle from zero
+        // preconditioned conjugate gradients, M^-1 = one V-cycle from a zero guess
         k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
         LAUNCH_CHECK(c);
-        F2D_TRY(read_scalars(c, S_RR, 2));
+        F2D_TRY(read_scalars(c, S_RR, 3));
         double ff = c->h_scal[S_FF];
-        relres = ff > 0 ? std::sqrt(c->h_scal[S_RR] / ff) : 0.0;
         if (ff == 0.0) {   // b == 0: the solution is 0 (up to the Neumann null space)
-            for (int col = 0; col < 2; col++) {
-                k_smooth0<true><<<grd(F.nx, F.ny), blk(), 0, st>>>(F, x, b, 0.0, col);
-                LAUNCH_CHECK(c);
-            }
+            F2D_TRY(zero_unknowns(c, F, x));
             conv = true;
-        } else if (!(relres > rtol)) conv = true;
+        } else {
+            relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
+            if (!(relres > rtol)) conv = true;
+        }
+        double best = relres;
+        double *pold = M.p, *pnew = M.p2;
+        const int slot = singular ? S_SUMR : -1;   // lazy projection r - mean(r)
         for (it = 0; !conv && it < maxit; it++) {
-            F2D_TRY(vcycle(c, M, M.z, M.r, 1.0, true));
-            k_dot<<<nblk, 256, 0, st>>>(F, M.r, M.z, c->d_part, c->d_count, S + (it == 0 ? S_RZ : S_RZNEW));
+            if (unfused) {
+                if (singular) { k_cg_project<<<nblk, 256, 0, st>>>(F, M.r, S, inv_n); LAUNCH_CHECK(c); }
+                F2D_TRY(vcycle_unfused(c, M, M.z, M.r, 1.0, true));
+                k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
+                LAUNCH_CHECK(c);
+            } else {
+                F2D_TRY(vcycle_fused(c, M, nullptr, M.r, 1.0, true, slot, true, M.z2));
+            }
+            k_cg_dir_apply<<<nblk, 256, 0, st>>>(F, unfused ? M.z : M.z2, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
+                                                 c->d_part, c->d_count);
             LAUNCH_CHECK(c);
-            k_cg_dir<<<nblk, 256, 0, st>>>(F, M.p, M.z, S, it == 0);
+            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pnew, M.q, S, S_RZ0 + (it & 1), c->d_part, c->d_count, S + S_RR);
             LAUNCH_CHECK(c);
-            if (it > 0) { k_cg_shift<<<1, 1, 0, st>>>(S); LAUNCH_CHECK(c); }
-            k_cg_apply<<<nblk, 256, 0, st>>>(F, M.p, M.q, c->d_part, c->d_count, S + S_PQ);
-            LAUNCH_CHECK(c);
-            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, M.p, M.q, S, c->d_part, c->d_count, S + S_RR);
-            LAUNCH_CHECK(c);
-            F2D_TRY(read_scalars(c, S_RR, 1));
-            relres = std::sqrt(c->h_scal[S_RR] / ff);
+            std::swap(pold, pnew);
+            F2D_TRY(read_scalars(c, S_RR, 2));
+            relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
             if (!(relres > rtol)) { conv = true; it++; break; }
+            best = std::min(best, relres);
+            if (!(relres < 1e6 * best)) { it++; break; }   // diverging: give up, report
         }
     }
     c->nsolves++;
@@ -891,28 +1216,37 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
         int n = pass == 0 ? 2 : reps;
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < n; r++) {
-            if (k == "mg.smooth_halfsweep") {
+            if (k == "mg.down0") {
+                // fused down leg, level 0: R r bits, W z + b1 (fp32, 1/4 of the points)
+                F2D_TRY((launch_down0<2, true>(c, M, M.z, M.z, M.r, 1.0, -1)));
+                *bytes = npts * (8 + 1 + 8 + 1);
+            } else if (k == "mg.up0") {
+                // fused up leg, level 0: R z r bits x1 (fp32, 1/4), W z2
+                F2D_TRY((launch_up0<2, true>(c, M, M.z, M.z2, M.r, 1.0, -1)));
+                *bytes = npts * (8 + 8 + 1 + 1 + 8);
+            } else if (k == "mg.down1") {
+                F2D_TRY((coarse_down<2>(c, M, 1)));
+                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (4 * 4 + 1 + 4 + 1);
+            } else if (k == "mg.up1") {
+                F2D_TRY((coarse_up<2>(c, M, 1)));
+                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (5 * 4 + 1 + 1 + 4);
+            } else if (k == "mg.tail") {
+                F2D_TRY(launch_tail(c, M));
+                *bytes = 0;
+            } else if (k == "mg.smooth_halfsweep") {
                 // one colour: R x(other colour) f(own) W x(own), 1 mask byte per updated point
                 k_smooth0<false><<<g0, blk(), 0, c->stream>>>(F, M.z, M.r, 1.0, r & 1);
                 *bytes = npts * (1.5 * 8 + 0.5);
-            } else if (k == "mg.residual") {
-                k_resid0<<<g0, blk(), 0, c->stream>>>(F, M.z, M.r, 1.0, M.q);
-                *bytes = npts * (3 * 8 + 1);
-            } else if (k == "mg.restrict") {
-                CoarseView C1 = view_of(M.lev[1], F.periodic, F.dirichlet);
-                k_restrict0<<<grd(C1.nx, C1.ny), blk(), 0, c->stream>>>(F, M.q, C1, M.lev[1].b);
-                *bytes = npts * (8 + 1 + 2.0 + 0.25);
-            } else if (k == "mg.prolong") {
-                k_prolong0<<<g0, blk(), 0, c->stream>>>(F, M.z, view_of(M.lev[1], F.periodic, F.dirichlet), M.lev[1].x);
-                *bytes = npts * (2 * 8 + 1 + 2.0);
-            } else if (k == "cg.apply_dot") {
-                k_cg_apply<<<nblk, 256, 0, c->stream>>>(F, M.p, M.q, c->d_part, c->d_count, c->d_scal + S_TMP);
-                *bytes = npts * (2 * 8 + 1);
+                LAUNCH_CHECK(c);
+            } else if (k == "cg.dir_apply") {
+                k_cg_dir_apply<<<nblk, 256, 0, c->stream>>>(F, M.z, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
+                *bytes = npts * (4 * 8 + 1);
+                LAUNCH_CHECK(c);
             } else if (k == "cg.update") {
-                k_cg_update<<<nblk, 256, 0, c->stream>>>(F, M.z, M.r, M.p, M.q, c->d_scal + 16, c->d_part, c->d_count, c->d_scal + S_TMP);
+                k_cg_update<<<nblk, 256, 0, c->stream>>>(F, M.z, M.r, M.p, M.q, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP);
                 *bytes = npts * (6 * 8 + 1);
+                LAUNCH_CHECK(c);
             } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
-            LAUNCH_CHECK(c);
         }
     }
     F2D_CUDA(cudaEventRecord(c->ev1, c->stream));

@@ -1,0 +1,396 @@
+// Shared-memory tile kernels of the multigrid V-cycle.
+//
+// One V-cycle leg on one level is ONE kernel:
+//   k_mg_down : nu1 red-black Gauss-Seidel sweeps + residual + restriction
+//               (R = P^T) to the next coarser level
+//   k_mg_up   : prolongation of the coarse correction + nu2 sweeps (+ the CG
+//               dot products r.z and 1.z on the fine level)
+// instead of one kernel per half-sweep.  A CTA owns a window of WJ x 64 points
+// in shared memory; each half-sweep is exact on a region one ring smaller than
+// the previous one (the domain of dependence of red-black relaxation grows by
+// one point per half-sweep), so the interior TJ x TI = (WJ-2H) x (64-2H)
+// points come out bit-identical to grid-wide sweeps, whatever the tiling.  HBM
+// traffic per leg drops from ~(4 nu + 3) array passes to one read of the
+// inputs and one write of the outputs.
+//
+// Shared-memory layout: the two colours of the checkerboard are stored apart,
+// [colour][row][k] with 32 entries per row, so a warp that relaxes one colour
+// of one row touches 32 consecutive words of each operand: no bank conflicts.
+//   row parity rp = colour of column 0 of that row
+//   colour c point k sits at column b = 2k + (c ^ rp)
+//   its W / E neighbours are (1-c, k + o - 1) and (1-c, k + o), o = c ^ rp
+//   its S / N neighbours are (1-c, row -+ 1, k)
+//
+// A leg that reads x with a halo must not write it in place (a neighbouring CTA
+// may already have stored its interior): xin / xout are distinct buffers; only
+// the zero-guess down leg, which never reads x, may alias them.
+//
+// FINE  (level 0): fp64, operator from one byte of mask bits per point
+// COARSE (l >= 1): CT (fp32) arrays of face couplings and inverse diagonals.
+#pragma once
+#include "engine.cuh"
+#include "reduce.cuh"
+
+namespace f2d {
+
+constexpr int TW = 64;    // window width in points
+constexpr int TK = 32;    // points of one colour per window row
+constexpr int TILE_THREADS = 256;
+
+__host__ __device__ constexpr int halo_down(int nu, bool zero) { return zero ? 2 * nu + 1 : 2 * nu + 2; }
+__host__ __device__ constexpr int halo_up(int nu) { return 2 * nu; }
+
+template <typename T>
+struct CoarseArrays {       // level l >= 1, halo-padded (ny+2) x pitch
+    int ny, nx, pitch, periodic, dirichlet;
+    const T *cx, *cy, *dinv;
+    const uint8_t *code;
+};
+
+__device__ __forceinline__ int wrap_mod(int i, int n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+// ---- level descriptors: how a window point maps to global memory ------------
+struct FineLevel {
+    FineView F;
+    __device__ __forceinline__ int ny() const { return F.ny; }
+    __device__ __forceinline__ int nx() const { return F.nx; }
+    __device__ __forceinline__ int dirichlet() const { return F.dirichlet; }
+    // global index of logical (j,i) or -1
+    __device__ __forceinline__ long index(int j, int i) const {
+        if (j < 0 || j >= F.ny) return -1;
+        if (F.periodic) i = wrap_mod(i, F.nx);
+        else if (i < 0 || i >= F.nx) return -1;
+        int aj = F.oj + j, ai = F.oi + i;
+        if (aj < 0 || aj >= F.n2 || ai < 0 || ai >= F.n1) return -1;
+        return (long)aj * F.n1 + ai;
+    }
+};
+
+template <typename T>
+struct CoarseLevel {
+    CoarseArrays<T> A;
+    __device__ __forceinline__ int ny() const { return A.ny; }
+    __device__ __forceinline__ int nx() const { return A.nx; }
+    __device__ __forceinline__ int dirichlet() const { return A.dirichlet; }
+    __device__ __forceinline__ long index(int j, int i) const {
+        if (j < 0 || j >= A.ny) return -1;
+        if (A.periodic) i = wrap_mod(i, A.nx);
+        else if (i < 0 || i >= A.nx) return -1;
+        return (long)(j + 1) * A.pitch + i + 1;
+    }
+};
+
+// ---- shared-memory window -----------------------------------------------------
+template <typename T, bool FINE, int WJ>
+struct Window {
+    T *X, *Fv;              // [2][WJ][TK]
+    T *CX, *CY, *DI;        // COARSE only
+    uint8_t *B;             // mask / parent bits
+    T *tab_dinv, *tab_diag; // FINE only: 32 entries indexed by bits & 31
+    T cxf, cyf;             // FINE couplings
+
+    __device__ __forceinline__ static int at(int c, int a, int k) { return (c * WJ + a) * TK + k; }
+
+    __host__ __device__ static constexpr size_t bytes() {
+        size_t n = (size_t)2 * WJ * TK;
+        return (FINE ? 2 : 5) * n * sizeof(T) + n + (FINE ? 64 * sizeof(T) : 0);
+    }
+
+    __device__ void carve(unsigned char *smem) {
+        size_t n = (size_t)2 * WJ * TK;
+        T *p = reinterpret_cast<T *>(smem);
+        X = p; p += n;
+        Fv = p; p += n;
+        CX = CY = DI = tab_dinv = tab_diag = nullptr;
+        if (!FINE) { CX = p; p += n; CY = p; p += n; DI = p; p += n; }
+        else { tab_dinv = p; p += 32; tab_diag = p; p += 32; }
+        B = reinterpret_cast<uint8_t *>(p);
+    }
+
+    // one red-black half-sweep of colour `col` on the ring-`m` interior
+    template <bool NO_NEIGHBOURS>
+    __device__ __forceinline__ void relax(int col, int m, int par0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
+        for (int a = m + warp; a < WJ - m; a += nw) {
+            int rp = (par0 + a) & 1, o = col ^ rp, b = 2 * k + o;
+            if (b < m || b >= TW - m) continue;
+            int p = at(col, a, k);
+            T acc = Fv[p];
+            if (!NO_NEIGHBOURS) {
+                int q = at(1 - col, a, k);
+                T xw = X[q + o - 1], xe = X[q + o], xs = X[q - TK], xn = X[q + TK];
+                if constexpr (FINE) acc += cxf * (xw + xe) + cyf * (xs + xn);
+                else acc += CX[p] * xw + CX[q + o] * xe + CY[p] * xs + CY[q + TK] * xn;
+            }
+            if constexpr (FINE) X[p] = acc * tab_dinv[B[p] & 31];
+            else X[p] = acc * DI[p];
+        }
+    }
+
+    // residual, pre-divided by the prolongation normaliser, into Fv (ring m)
+    __device__ __forceinline__ void residual(int m, int par0, int dirichlet) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
+        for (int a = m + warp; a < WJ - m; a += nw) {
+            int rp = (par0 + a) & 1;
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+                int o = col ^ rp, b = 2 * k + o;
+                if (b < m || b >= TW - m) continue;
+                int p = at(col, a, k), q = at(1 - col, a, k);
+                T xw = X[q + o - 1], xe = X[q + o], xs = X[q - TK], xn = X[q + TK];
+                uint8_t bits = B[p];
+                T off, diag;
+                if constexpr (FINE) {
+                    off = cxf * (xw + xe) + cyf * (xs + xn);
+                    diag = tab_diag[bits & 31];
+                } else {
+                    off = CX[p] * xw + CX[q + o] * xe + CY[p] * xs + CY[q + TK] * xn;
+                    T di = DI[p];
+                    diag = di != T(0) ? T(1) / di : T(0);
+                }
+                T w16 = dirichlet ? T(16) : T(9 + ((bits & NB_PJ) ? 3 : 0) + ((bits & NB_PI) ? 3 : 0) +
+                                              ((bits & NB_PJI) ? 1 : 0));
+                T res = (bits & NB_SELF) ? (Fv[p] - (diag * X[p] - off)) / w16 : T(0);
+                Fv[p] = res;    // each thread only overwrites what it alone reads
+            }
+        }
+    }
+
+    __device__ __forceinline__ T &Xat(int par0, int a, int b) {
+        int c = (par0 + a + b) & 1;
+        return X[at(c, a, b >> 1)];
+    }
+    __device__ __forceinline__ T &Fat(int par0, int a, int b) {
+        int c = (par0 + a + b) & 1;
+        return Fv[at(c, a, b >> 1)];
+    }
+};
+
+// fill the FINE inverse-diagonal tables (bits & 31 -> diag, 1/diag)
+template <typename T>
+__device__ __forceinline__ void fill_tables(const FineView &F, T *tab_dinv, T *tab_diag) {
+    if (threadIdx.x < 32) {
+        int c = threadIdx.x;
+        double d = 0.0;
+        if (c & NB_SELF) {
+            if (F.dirichlet) d = 2.0 * (F.cx + F.cy) + F.shift;
+            else d = F.cx * (((c & NB_W) ? 1 : 0) + ((c & NB_E) ? 1 : 0)) +
+                     F.cy * (((c & NB_S) ? 1 : 0) + ((c & NB_N) ? 1 : 0)) + F.shift;
+        }
+        tab_diag[c] = (T)d;
+        tab_dinv[c] = d > 0.0 ? (T)(1.0 / d) : T(0);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// DOWN leg.   x <- NU sweeps (R,B) on  L x = f ;  bc <- P^T (f - L x)
+//   FINE : f = fscale * fin - fshift (fshift = mean of fin when the operator is
+//          singular and CG asks for the projected residual), x in the (n2,n1)
+//          array; ZERO = first guess is zero (x is only written).
+//   TC   : element type of the next coarser level
+// ---------------------------------------------------------------------------
+template <typename T, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
+          const double *__restrict__ scal, int sumr_slot, double inv_n,
+          int nyc, int nxc, int pitchc, TC *__restrict__ bc) {
+    constexpr int H = halo_down(NU, ZERO);
+    constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
+    extern __shared__ __align__(16) unsigned char smem[];
+    Window<T, FINE, WJ> W;
+    W.carve(smem);
+    const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
+    const int dirichlet = L.dirichlet();
+    T fshift = T(0);
+    if constexpr (FINE) {
+        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+        fill_tables<T>(L.F, W.tab_dinv, W.tab_diag);
+        if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
+    }
+    // ---- load the window
+    for (int a = warp; a < WJ; a += nw) {
+        int rp = (par0 + a) & 1, j = wj0 + a;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            long g = L.index(j, wi0 + b);
+            T fv = T(0), xv = T(0);
+            uint8_t bits = 0;
+            if constexpr (FINE) {
+                if (g >= 0) {
+                    bits = L.F.nb[g];
+                    if (bits & NB_SELF) { fv = (T)fscale * fin[g] - fshift; if (!ZERO) xv = xin[g]; }
+                }
+            } else {
+                T cxv = T(0), cyv = T(0), div = T(0);
+                if (g >= 0) {
+                    bits = L.A.code[g];
+                    fv = fin[g];
+                    if (!ZERO) xv = xin[g];
+                    cxv = L.A.cx[g]; cyv = L.A.cy[g]; div = L.A.dinv[g];
+                }
+                W.CX[p] = cxv; W.CY[p] = cyv; W.DI[p] = div;
+            }
+            W.B[p] = bits; W.Fv[p] = fv; W.X[p] = xv;
+        }
+    }
+    __syncthreads();
+    // ---- NU sweeps, red then black
+#pragma unroll
+    for (int hs = 0; hs < 2 * NU; hs++) {
+        if (ZERO && hs == 0) W.template relax<true>(0, 0, par0);
+        else W.template relax<false>(hs & 1, ZERO ? hs : hs + 1, par0);
+        __syncthreads();
+    }
+    // ---- residual on the tile +- 1, then write x and the restricted residual
+    W.residual(H - 1, par0, dirichlet);
+    for (int a = H + warp; a < WJ - H; a += nw) {
+        int rp = (par0 + a) & 1, j = wj0 + a;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            if (b < H || b >= TW - H) continue;
+            if (!(W.B[p] & NB_SELF)) continue;
+            if (j >= L.ny() || wi0 + b >= L.nx()) continue;   // periodic images are another tile's
+            long g = L.index(j, wi0 + b);
+            if (g >= 0) xout[g] = W.X[p];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (TJ / 2) * (TI / 2); t += TILE_THREADS) {
+        int cj = t / (TI / 2), ci = t - cj * (TI / 2);
+        int J = tj0 / 2 + cj, I = ti0 / 2 + ci;
+        if (J >= nyc || I >= nxc) continue;
+        int a0 = 2 * J - wj0, b0 = 2 * I - wi0;
+        T acc = T(0);
+#pragma unroll
+        for (int da = -1; da <= 2; da++) {
+            T wy = (da == 0 || da == 1) ? T(3) : T(1);
+#pragma unroll
+            for (int db = -1; db <= 2; db++) {
+                T wx = (db == 0 || db == 1) ? T(3) : T(1);
+                acc += wy * wx * W.Fat(par0, a0 + da, b0 + db);
+            }
+        }
+        bc[(long)(J + 1) * pitchc + I + 1] = (TC)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
+// ---------------------------------------------------------------------------
+template <typename T, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
+        const double *__restrict__ scal, int sumr_slot, double inv_n,
+        int nyc, int nxc, int pitchc, int periodic_c, const TC *__restrict__ xc,
+        double *part, unsigned int *count, double *out) {
+    constexpr int H = halo_up(NU);
+    constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
+    constexpr int CJ = WJ / 2 + 3, CI = TW / 2 + 3;
+    extern __shared__ __align__(16) unsigned char smem[];
+    Window<T, FINE, WJ> W;
+    W.carve(smem);
+    T *XC = reinterpret_cast<T *>(smem + ((Window<T, FINE, WJ>::bytes() + 15) & ~size_t(15)));
+    const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
+    const int dirichlet = L.dirichlet();
+    T fshift = T(0);
+    if constexpr (FINE) {
+        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+        fill_tables<T>(L.F, W.tab_dinv, W.tab_diag);
+        if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
+    }
+    // ---- coarse window
+    const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
+    for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
+        int a = t / CI, b = t - a * CI;
+        int J = cj0 + a, I = ci0 + b;
+        T v = T(0);
+        if (J >= 0 && J < nyc) {
+            if (periodic_c) I = wrap_mod(I, nxc);
+            if (I >= 0 && I < nxc) v = (T)xc[(long)(J + 1) * pitchc + I + 1];
+        }
+        XC[t] = v;
+    }
+    // ---- fine window
+    for (int a = warp; a < WJ; a += nw) {
+        int rp = (par0 + a) & 1, j = wj0 + a;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            long g = L.index(j, wi0 + b);
+            T fv = T(0), xv = T(0);
+            uint8_t bits = 0;
+            if constexpr (FINE) {
+                if (g >= 0) {
+                    bits = L.F.nb[g];
+                    if (bits & NB_SELF) { fv = (T)fscale * fin[g] - fshift; xv = xin[g]; }
+                }
+            } else {
+                T cxv = T(0), cyv = T(0), div = T(0);
+                if (g >= 0) {
+                    bits = L.A.code[g];
+                    fv = fin[g];
+                    xv = xin[g];
+                    cxv = L.A.cx[g]; cyv = L.A.cy[g]; div = L.A.dinv[g];
+                }
+                W.CX[p] = cxv; W.CY[p] = cyv; W.DI[p] = div;
+            }
+            W.B[p] = bits; W.Fv[p] = fv; W.X[p] = xv;
+        }
+    }
+    __syncthreads();
+    // ---- prolongation on the whole window
+    for (int a = warp; a < WJ; a += nw) {
+        int rp = (par0 + a) & 1, j = wj0 + a;
+        int J0 = (j >> 1) - cj0, Jn = J0 + ((j & 1) ? 1 : -1);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            uint8_t bits = W.B[p];
+            if (!(bits & NB_SELF)) continue;
+            int i = wi0 + b;
+            int I0 = (i >> 1) - ci0, In = I0 + ((i & 1) ? 1 : -1);
+            T v = T(9) * XC[J0 * CI + I0] + T(3) * XC[Jn * CI + I0] + T(3) * XC[J0 * CI + In] + XC[Jn * CI + In];
+            T w16 = dirichlet ? T(16) : T(9 + ((bits & NB_PJ) ? 3 : 0) + ((bits & NB_PI) ? 3 : 0) +
+                                          ((bits & NB_PJI) ? 1 : 0));
+            W.X[p] += v / w16;
+        }
+    }
+    __syncthreads();
+    // ---- NU sweeps, black then red
+#pragma unroll
+    for (int hs = 0; hs < 2 * NU; hs++) {
+        W.template relax<false>(1 - (hs & 1), hs + 1, par0);
+        __syncthreads();
+    }
+    // ---- write the interior (+ dots)
+    double acc[2] = {0.0, 0.0};
+    for (int a = H + warp; a < WJ - H; a += nw) {
+        int rp = (par0 + a) & 1, j = wj0 + a;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            if (b < H || b >= TW - H) continue;
+            if (!(W.B[p] & NB_SELF)) continue;
+            if (j >= L.ny() || wi0 + b >= L.nx()) continue;   // periodic images are another tile's
+            long g = L.index(j, wi0 + b);
+            if (g < 0) continue;
+            T xv = W.X[p];
+            xout[g] = xv;
+            if (DOT) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
+        }
+    }
+    if (DOT) grid_reduce<OpSum, 2>(acc, part, count, out);
+}
+
+}  // namespace f2d

@@ -153,8 +153,8 @@ int f2d_timer_stop(f2d_ctx *ctx, float *ms);
 /* bench.py: time ONE kernel alone (`reps` launches between two events on the
  * context's stream; average ms per launch) and report its algorithmic bytes
  * per launch.  Names: advection, rk_update, divergence, project_diag,
- * mg.smooth_halfsweep, mg.residual, mg.restrict, mg.prolong, cg.apply_dot,
- * cg.update.  Clobbers scratch arrays and diagnostics: call it last. */
+ * mg.down0, mg.up0, mg.down1, mg.up1, mg.tail, cg.dir_apply, cg.update.
+ * Clobbers scratch arrays and diagnostics: call it last. */
 int f2d_bench_kernel(f2d_ctx *ctx, const char *name, int reps, float *ms, double *alg_bytes);
 /* number of kernels this context has launched so far */
 int f2d_launch_count(f2d_ctx *ctx, int64_t *count);

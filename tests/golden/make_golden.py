@@ -233,6 +233,25 @@ def case_lock_exchange():
     run_case("lock_exchange", kw, ic=lock_ic)
 
 
+def run_to_tend():
+    """tests/test_models.py:9-15: default 40x40 Euler dipole, model.run() to
+    tend = 10 with the adaptive CFL step.  The reference's own assertion
+    (ite == 25) is stale against its current default cfl = 0.9; the live code
+    gives the count stored here."""
+    p = make_param(model="euler", tend=10)
+    model = f2d.Model(p)
+    dipole_ic(model, 0.5, 0.5, 0.05, 0.05)
+    out = {}
+    snapshot(model.state, "init", out)
+    model.run()
+    snapshot(model.state, "final", out)
+    out["meta"] = np.array(json.dumps(dict(param=dict(model="euler", tend=10), ite=model.time.ite,
+                                           t=model.time.t, dt_last=model.time.dt)))
+    path = os.path.join(HERE, "run_euler40.npz")
+    np.savez_compressed(path, **out)
+    print(f"run_euler40: ite={model.time.ite} t={model.time.t} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
 # ---------------------------------------------------- per-kernel vectors ---
 def ops_vectors():
     """weno.VortexForce / InnerProduct / CompFlux for all 4 methods on a masked,
@@ -369,7 +388,7 @@ if __name__ == "__main__":
     todo = [case_euler40, case_vortex, case_vortex_triangle, case_disc_island, case_xper_noslip,
             case_euler_enrk3_upwind, case_euler_centered_ef, case_euler_cweno,
             case_rsw, case_rsw_islands, case_qgrsw_topo, case_qgrsw_islands,
-            case_warm_bubble, case_lock_exchange, ops_vectors, solve_vectors, mesh_vectors]
+            case_warm_bubble, case_lock_exchange, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
     for fn in todo:
         if which is None or fn.__name__ in which:
             fn()

@@ -1,0 +1,136 @@
+"""CPU-only checks of the boundary: the shared libraries build, load, and export
+every symbol include/f2d.h declares; the host mirror keeps the reference's names
+and argument checks; no compute is attempted without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "f2d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(f2d_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from fluids2d_b200 import build
+    return build.build_all()
+
+
+def test_header_symbols_are_exported(built):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for path in built:
+        lib = ctypes.CDLL(path)
+        for s in syms:
+            assert hasattr(lib, s), (os.path.basename(path), s)
+
+
+def test_binding_covers_header(built):
+    from fluids2d_b200 import _cabi
+    assert sorted(_cabi.SIGNATURES) == declared_symbols()
+    lib = _cabi.load()
+    assert lib.f2d_version() == 100
+
+
+def test_config_struct_layout_matches_header():
+    """field order/types of f2d_config in the header == the ctypes Structure"""
+    from fluids2d_b200 import _cabi
+    txt = open(os.path.join(ROOT, "include", "f2d.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} f2d_config;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        typ, rest = decl.split(None, 1)
+        for n in rest.split(","):
+            names.append((n.strip().split("[")[0], typ))
+    got = [(n, {"c_int": "int32_t", "c_double": "double"}.get(
+        getattr(t, "_type_", t).__name__ if hasattr(t, "_length_") else t.__name__, t.__name__))
+        for n, t in _cabi.Config._fields_]
+    assert [n for n, _ in got] == [n for n, _ in names]
+    assert [t for _, t in got] == [t for _, t in names]
+
+
+def test_no_cpu_fallback(built):
+    """without a device the product path raises; it never computes on the host"""
+    import fluids2d_b200 as f2d
+    from fluids2d_b200._cabi import F2DError
+    n = ctypes.c_int()
+    lib = __import__("fluids2d_b200._cabi", fromlist=["load"]).load()
+    if lib.f2d_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    f2d.Param._quiet = True
+    with pytest.raises(F2DError):
+        f2d.Model(f2d.Param())
+
+
+def test_param_surface():
+    import fluids2d_b200 as f2d
+    f2d.Param._quiet = True
+    p = f2d.Param()
+    # reference defaults (param.py:13-59)
+    assert (p.model, p.nx, p.ny, p.halowidth, p.integrator, p.cfl, p.maxorder) == \
+           ("euler", 40, 40, 3, "rk3", 0.9, 6)
+    assert (p.compflux, p.vortexforce, p.innerproduct, p.nthreads) == ("weno", "weno", "weno", 1)
+    p.check()
+    p.bogus = 1
+    with pytest.raises(AssertionError):
+        p.check()
+    q = f2d.Param()
+    q.add_parameter("Q")
+    q.Q = 0.05
+    q.check()
+    q.model = "nope"
+    with pytest.raises(AssertionError):
+        q.check()
+
+
+def test_out_of_scope_models_raise():
+    import fluids2d_b200 as f2d
+    f2d.Param._quiet = True
+    p = f2d.Param()
+    p.model = "hydrostatic"
+    with pytest.raises(NotImplementedError):
+        f2d.Model(p)
+    p = f2d.Param()
+    p.integrator = "LFRA"
+    from fluids2d_b200._cabi import config_from_param
+    with pytest.raises(NotImplementedError):
+        config_from_param(p)
+
+
+def test_time_is_kahan_compensated():
+    import fluids2d_b200 as f2d
+    from fluids2d_b200.timeline import Time
+    f2d.Param._quiet = True
+    p = f2d.Param()
+    p.dt = 0.1
+    t = Time(p)
+    for _ in range(10):
+        t.pushforward()
+    assert t.t == 1.0 and t.ite == 10
+
+
+def test_rk_coefficients_are_the_references_doubles():
+    from fluids2d_b200.integrators import rk_coefficients
+    dt = 0.3281
+    assert rk_coefficients("rk3", dt) == [(dt,), (-3 * dt / 4, dt / 4), (-dt / 12, -dt / 12, 2 * dt / 3)]
+    assert rk_coefficients("ef", dt) == [(dt,)]
+    assert len(rk_coefficients("enrk3", dt)[2]) == 3
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fluids2d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle harness", ""), os.path.join(dirpath, f)
