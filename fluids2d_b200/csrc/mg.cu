@@ -191,11 +191,11 @@ k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const CT *__restric
     x[idx] += v / w16_of(c, F.dirichlet);
 }
 
-// 1-D grid-stride walk over the fine window (for kernels with reductions)
-#define FINE_LOOP(F)                                                              \
-    long _n0 = (long)(F).ny * (F).nx;                                             \
-    for (long _t = (long)blockIdx.x * blockDim.x + threadIdx.x; _t < _n0;         \
-         _t += (long)gridDim.x * blockDim.x)
+// 2-D grid-stride walk over the fine window (for kernels with reductions):
+// blockIdx.y strides over rows, threads over columns; no integer divisions
+#define FINE_LOOP(F)                                                                      \
+    for (int j = blockIdx.y; j < (F).ny; j += gridDim.y)                                  \
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (F).nx; i += gridDim.x * blockDim.x)
 
 // r = f - L x ; rr = r.r ; ff = f.f ; sum = 1.r      (CG start / convergence check)
 __global__ void __launch_bounds__(256)
@@ -203,7 +203,6 @@ k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ 
            double *__restrict__ r, double *part, unsigned int *count, double *out) {
     double v[3] = {0.0, 0.0, 0.0};
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         uint8_t c = F.nb[idx];
@@ -227,7 +226,6 @@ __global__ void __launch_bounds__(256)
 k_cg_project(FineView F, double *__restrict__ r, const double *__restrict__ scal, double inv_n) {
     double mean = scal[S_SUMR] * inv_n;
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         if (!(F.nb[idx] & NB_SELF)) continue;
@@ -241,7 +239,6 @@ k_cg_apply(FineView F, const double *__restrict__ p, double *__restrict__ q, dou
            unsigned int *count, double *out) {
     double v[1] = {0.0};
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         uint8_t c = F.nb[idx];
@@ -265,7 +262,6 @@ k_cg_update(FineView F, double *__restrict__ x, double *__restrict__ r,
     double alpha = pq != 0.0 ? scal[rz_slot] / pq : 0.0;
     double v[2] = {0.0, 0.0};
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         if (!(F.nb[idx] & NB_SELF)) continue;
@@ -287,7 +283,6 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
     double mr = sumr_slot >= 0 ? scal[sumr_slot] * inv_n : 0.0;
     double v[2] = {0.0, 0.0};
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         if (!(F.nb[idx] & NB_SELF)) continue;
@@ -313,7 +308,6 @@ k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restric
     if (it > 0) { double rzold = scal[S_RZ0 + ((it - 1) & 1)]; beta = rzold != 0.0 ? rznew / rzold : 0.0; }
     double v[1] = {0.0};
     FINE_LOOP(F) {
-        int j = (int)(_t / F.nx), i = (int)(_t - (long)j * F.nx);
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         uint8_t c = F.nb[idx];
@@ -332,7 +326,7 @@ k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restric
         v[0] += pc * qv;
     }
     grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
-    if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_RZ0 + (it & 1)] = rznew;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) scal[S_RZ0 + (it & 1)] = rznew;
 }
 
 // y = A x = -L x on the unknowns, 0 elsewhere inside the window
@@ -604,6 +598,12 @@ __global__ void k_solver_mask(const int8_t *__restrict__ m, int8_t *__restrict__
 
 // ------------------------------------------------------------------- host ---
 static dim3 blk() { return dim3(64, 4); }
+// grid of the CG vector kernels: 256-thread blocks, x over columns, y strides rows
+static dim3 cg_grid(const f2d_ctx *c, const FineView &F) {
+    int gx = std::max(1, std::min((F.nx + 255) / 256, 16));
+    int gy = std::max(1, std::min(F.ny, (c->nsm * 8) / gx));
+    return dim3(gx, gy);
+}
 static dim3 grd(int nx, int ny) { return dim3((nx + 63) / 64, (ny + 3) / 4); }
 
 static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
@@ -917,7 +917,7 @@ static int launch_up0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout,
     const FineView &F = M.fine;
     FineLevel L{F};
     auto kern = k_mg_up<double, CT, true, DOT, NU, WJ, FineLevel>;
-    size_t smem = ((Window<double, true, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(double);
+    size_t smem = ((Window<double, true, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
     static bool once = false;
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
@@ -1115,7 +1115,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const double rtol = c->cfg.solver_rtol > 0 ? c->cfg.solver_rtol : 1e-12;
     const int maxit = c->cfg.solver_maxit > 0 ? c->cfg.solver_maxit : 100;
     const double fscale = -bscale;   // L = -A
-    const int nblk = c->nsm * 8;
+    const dim3 nblk = cg_grid(c, F);
     const bool singular = !F.dirichlet && F.shift == 0.0;
     const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
     const double N = (double)M.nunknown, inv_n = 1.0 / N;
@@ -1211,7 +1211,7 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
     std::string k(name);
     double npts = (double)F.ny * F.nx;
     dim3 g0 = grd(F.nx, F.ny);
-    const int nblk = c->nsm * 8;
+    const dim3 nblk = cg_grid(c, F);
     for (int pass = 0; pass < 2; pass++) {
         int n = pass == 0 ? 2 : reps;
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));

@@ -35,7 +35,8 @@ namespace f2d {
 
 constexpr int TW = 64;    // window width in points
 constexpr int TK = 32;    // points of one colour per window row
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_WARPS = TILE_THREADS / 32;
 
 __host__ __device__ constexpr int halo_down(int nu, bool zero) { return zero ? 2 * nu + 1 : 2 * nu + 2; }
 __host__ __device__ constexpr int halo_up(int nu) { return 2 * nu; }
@@ -51,21 +52,34 @@ __device__ __forceinline__ int wrap_mod(int i, int n) {
     i %= n;
     return i < 0 ? i + n : i;
 }
+// a window is at most TW + a few columns wide: one wrap is enough unless the
+// grid itself is narrower than the window
+__device__ __forceinline__ int wrap_col(int i, int n) {
+    if (n >= 2 * TW) {
+        if (i < 0) i += n;
+        else if (i >= n) i -= n;
+        return i;
+    }
+    return wrap_mod(i, n);
+}
 
 // ---- level descriptors: how a window point maps to global memory ------------
+// row(j): offset of logical (j, 0) or -1;  col(i): offset to add, or -1
 struct FineLevel {
     FineView F;
     __device__ __forceinline__ int ny() const { return F.ny; }
     __device__ __forceinline__ int nx() const { return F.nx; }
     __device__ __forceinline__ int dirichlet() const { return F.dirichlet; }
-    // global index of logical (j,i) or -1
-    __device__ __forceinline__ long index(int j, int i) const {
-        if (j < 0 || j >= F.ny) return -1;
-        if (F.periodic) i = wrap_mod(i, F.nx);
+    __device__ __forceinline__ long row(int j) const {
+        int aj = F.oj + j;
+        if (j < 0 || j >= F.ny || aj < 0 || aj >= F.n2) return -1;
+        return (long)aj * F.n1 + F.oi;
+    }
+    __device__ __forceinline__ int col(int i) const {
+        if (F.periodic) i = wrap_col(i, F.nx);
         else if (i < 0 || i >= F.nx) return -1;
-        int aj = F.oj + j, ai = F.oi + i;
-        if (aj < 0 || aj >= F.n2 || ai < 0 || ai >= F.n1) return -1;
-        return (long)aj * F.n1 + ai;
+        int ai = F.oi + i;
+        return (ai < 0 || ai >= F.n1) ? -1 : i;
     }
 };
 
@@ -75,11 +89,13 @@ struct CoarseLevel {
     __device__ __forceinline__ int ny() const { return A.ny; }
     __device__ __forceinline__ int nx() const { return A.nx; }
     __device__ __forceinline__ int dirichlet() const { return A.dirichlet; }
-    __device__ __forceinline__ long index(int j, int i) const {
+    __device__ __forceinline__ long row(int j) const {
         if (j < 0 || j >= A.ny) return -1;
-        if (A.periodic) i = wrap_mod(i, A.nx);
-        else if (i < 0 || i >= A.nx) return -1;
-        return (long)(j + 1) * A.pitch + i + 1;
+        return (long)(j + 1) * A.pitch + 1;
+    }
+    __device__ __forceinline__ int col(int i) const {
+        if (A.periodic) return wrap_col(i, A.nx);
+        return (i < 0 || i >= A.nx) ? -1 : i;
     }
 };
 
@@ -90,13 +106,16 @@ struct Window {
     T *CX, *CY, *DI;        // COARSE only
     uint8_t *B;             // mask / parent bits
     T *tab_dinv, *tab_diag; // FINE only: 32 entries indexed by bits & 31
+    T *tab_invw;            // 8 entries indexed by bits >> 5: 1 / prolongation normaliser
     T cxf, cyf;             // FINE couplings
+
+    static constexpr int ROWS_PER_WARP = (WJ + TILE_WARPS - 1) / TILE_WARPS;
 
     __device__ __forceinline__ static int at(int c, int a, int k) { return (c * WJ + a) * TK + k; }
 
     __host__ __device__ static constexpr size_t bytes() {
         size_t n = (size_t)2 * WJ * TK;
-        return (FINE ? 2 : 5) * n * sizeof(T) + n + (FINE ? 64 * sizeof(T) : 0);
+        return (FINE ? 2 : 5) * n * sizeof(T) + n + 72 * sizeof(T);
     }
 
     __device__ void carve(unsigned char *smem) {
@@ -104,17 +123,40 @@ struct Window {
         T *p = reinterpret_cast<T *>(smem);
         X = p; p += n;
         Fv = p; p += n;
-        CX = CY = DI = tab_dinv = tab_diag = nullptr;
+        CX = CY = DI = nullptr;
         if (!FINE) { CX = p; p += n; CY = p; p += n; DI = p; p += n; }
-        else { tab_dinv = p; p += 32; tab_diag = p; p += 32; }
+        tab_dinv = p; p += 32; tab_diag = p; p += 32; tab_invw = p; p += 8;
         B = reinterpret_cast<uint8_t *>(p);
+    }
+
+    // tables: FINE diagonal by open-face bits; prolongation normaliser by parent bits
+    __device__ __forceinline__ void fill_tables(const FineView *F, int dirichlet) {
+        int c = threadIdx.x;
+        if (FINE && c < 32) {
+            double d = 0.0;
+            if (c & NB_SELF) {
+                if (F->dirichlet) d = 2.0 * (F->cx + F->cy) + F->shift;
+                else d = F->cx * (((c & NB_W) ? 1 : 0) + ((c & NB_E) ? 1 : 0)) +
+                         F->cy * (((c & NB_S) ? 1 : 0) + ((c & NB_N) ? 1 : 0)) + F->shift;
+            }
+            tab_diag[c] = (T)d;
+            tab_dinv[c] = d > 0.0 ? (T)(1.0 / d) : T(0);
+        }
+        if (c >= 32 && c < 40) {
+            int b = c - 32;     // bit0 = NB_PJ, bit1 = NB_PI, bit2 = NB_PJI
+            double w = dirichlet ? 16.0 : 9.0 + 3.0 * (b & 1) + 3.0 * ((b >> 1) & 1) + ((b >> 2) & 1);
+            tab_invw[b] = (T)(1.0 / w);
+        }
     }
 
     // one red-black half-sweep of colour `col` on the ring-`m` interior
     template <bool NO_NEIGHBOURS>
     __device__ __forceinline__ void relax(int col, int m, int par0) {
-        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
-        for (int a = m + warp; a < WJ - m; a += nw) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; r++) {
+            int a = m + warp + r * TILE_WARPS;
+            if (a >= WJ - m) break;
             int rp = (par0 + a) & 1, o = col ^ rp, b = 2 * k + o;
             if (b < m || b >= TW - m) continue;
             int p = at(col, a, k);
@@ -130,10 +172,13 @@ struct Window {
         }
     }
 
-    // residual, pre-divided by the prolongation normaliser, into Fv (ring m)
-    __device__ __forceinline__ void residual(int m, int par0, int dirichlet) {
-        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
-        for (int a = m + warp; a < WJ - m; a += nw) {
+    // residual, pre-multiplied by 1/normaliser of the prolongation, into Fv (ring m)
+    __device__ __forceinline__ void residual(int m, int par0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; r++) {
+            int a = m + warp + r * TILE_WARPS;
+            if (a >= WJ - m) break;
             int rp = (par0 + a) & 1;
 #pragma unroll
             for (int col = 0; col < 2; col++) {
@@ -151,39 +196,72 @@ struct Window {
                     T di = DI[p];
                     diag = di != T(0) ? T(1) / di : T(0);
                 }
-                T w16 = dirichlet ? T(16) : T(9 + ((bits & NB_PJ) ? 3 : 0) + ((bits & NB_PI) ? 3 : 0) +
-                                              ((bits & NB_PJI) ? 1 : 0));
-                T res = (bits & NB_SELF) ? (Fv[p] - (diag * X[p] - off)) / w16 : T(0);
+                T res = (bits & NB_SELF) ? (Fv[p] - (diag * X[p] - off)) * tab_invw[bits >> 5] : T(0);
                 Fv[p] = res;    // each thread only overwrites what it alone reads
             }
         }
     }
 
-    __device__ __forceinline__ T &Xat(int par0, int a, int b) {
-        int c = (par0 + a + b) & 1;
-        return X[at(c, a, b >> 1)];
-    }
     __device__ __forceinline__ T &Fat(int par0, int a, int b) {
         int c = (par0 + a + b) & 1;
         return Fv[at(c, a, b >> 1)];
     }
-};
 
-// fill the FINE inverse-diagonal tables (bits & 31 -> diag, 1/diag)
-template <typename T>
-__device__ __forceinline__ void fill_tables(const FineView &F, T *tab_dinv, T *tab_diag) {
-    if (threadIdx.x < 32) {
-        int c = threadIdx.x;
-        double d = 0.0;
-        if (c & NB_SELF) {
-            if (F.dirichlet) d = 2.0 * (F.cx + F.cy) + F.shift;
-            else d = F.cx * (((c & NB_W) ? 1 : 0) + ((c & NB_E) ? 1 : 0)) +
-                     F.cy * (((c & NB_S) ? 1 : 0) + ((c & NB_N) ? 1 : 0)) + F.shift;
+    // global -> shared: every load of a thread is issued before its first use
+    template <bool LOAD_X, class Lev>
+    __device__ __forceinline__ void load(const Lev &L, const T *__restrict__ xin, const T *__restrict__ fin,
+                                         T fscale, T fshift, int wj0, int wi0, int par0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
+        constexpr int R = WJ / TILE_WARPS;
+        static_assert(WJ % TILE_WARPS == 0, "window rows must be a multiple of the warp count");
+        T fv[R][2], xv[R][2], cxv[R][2], cyv[R][2], div[R][2];
+        uint8_t bits[R][2];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            long rb = L.row(wj0 + warp + r * TILE_WARPS);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int ch = h ? c1 : c0;
+                bool ok = rb >= 0 && ch >= 0;
+                long g = ok ? rb + ch : 0;
+                fv[r][h] = xv[r][h] = cxv[r][h] = cyv[r][h] = div[r][h] = T(0);
+                bits[r][h] = 0;
+                if (ok) {
+                    if constexpr (FINE) {
+                        bits[r][h] = L.F.nb[g];
+                        fv[r][h] = fin[g];
+                        if (LOAD_X) xv[r][h] = xin[g];
+                    } else {
+                        bits[r][h] = L.A.code[g];
+                        fv[r][h] = fin[g];
+                        if (LOAD_X) xv[r][h] = xin[g];
+                        cxv[r][h] = L.A.cx[g]; cyv[r][h] = L.A.cy[g]; div[r][h] = L.A.dinv[g];
+                    }
+                }
+            }
         }
-        tab_diag[c] = (T)d;
-        tab_dinv[c] = d > 0.0 ? (T)(1.0 / d) : T(0);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int a = warp + r * TILE_WARPS, rp = (par0 + a) & 1;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int p = at(rp ^ h, a, k);
+                bool self = bits[r][h] & NB_SELF;
+                B[p] = bits[r][h];
+                if constexpr (FINE) {
+                    // masked entries of the field arrays may hold anything: select, do not multiply
+                    Fv[p] = self ? fscale * fv[r][h] - fshift : T(0);
+                    X[p] = self ? xv[r][h] : T(0);
+                } else {
+                    Fv[p] = fv[r][h];
+                    X[p] = xv[r][h];
+                    CX[p] = cxv[r][h]; CY[p] = cyv[r][h]; DI[p] = div[r][h];
+                }
+            }
+        }
     }
-}
+};
 
 // ---------------------------------------------------------------------------
 // DOWN leg.   x <- NU sweeps (R,B) on  L x = f ;  bc <- P^T (f - L x)
@@ -193,7 +271,7 @@ __device__ __forceinline__ void fill_tables(const FineView &F, T *tab_dinv, T *t
 //   TC   : element type of the next coarser level
 // ---------------------------------------------------------------------------
 template <typename T, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 2)
 k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
           const double *__restrict__ scal, int sumr_slot, double inv_n,
           int nyc, int nxc, int pitchc, TC *__restrict__ bc) {
@@ -205,41 +283,14 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
     const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
-    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
-    const int dirichlet = L.dirichlet();
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     T fshift = T(0);
     if constexpr (FINE) {
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        fill_tables<T>(L.F, W.tab_dinv, W.tab_diag);
+        W.fill_tables(&L.F, L.dirichlet());
         if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
-    }
-    // ---- load the window
-    for (int a = warp; a < WJ; a += nw) {
-        int rp = (par0 + a) & 1, j = wj0 + a;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
-            long g = L.index(j, wi0 + b);
-            T fv = T(0), xv = T(0);
-            uint8_t bits = 0;
-            if constexpr (FINE) {
-                if (g >= 0) {
-                    bits = L.F.nb[g];
-                    if (bits & NB_SELF) { fv = (T)fscale * fin[g] - fshift; if (!ZERO) xv = xin[g]; }
-                }
-            } else {
-                T cxv = T(0), cyv = T(0), div = T(0);
-                if (g >= 0) {
-                    bits = L.A.code[g];
-                    fv = fin[g];
-                    if (!ZERO) xv = xin[g];
-                    cxv = L.A.cx[g]; cyv = L.A.cy[g]; div = L.A.dinv[g];
-                }
-                W.CX[p] = cxv; W.CY[p] = cyv; W.DI[p] = div;
-            }
-            W.B[p] = bits; W.Fv[p] = fv; W.X[p] = xv;
-        }
-    }
+    } else W.fill_tables(nullptr, L.dirichlet());
+    W.template load<!ZERO>(L, xin, fin, (T)fscale, fshift, wj0, wi0, par0);
     __syncthreads();
     // ---- NU sweeps, red then black
 #pragma unroll
@@ -249,17 +300,24 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
         __syncthreads();
     }
     // ---- residual on the tile +- 1, then write x and the restricted residual
-    W.residual(H - 1, par0, dirichlet);
-    for (int a = H + warp; a < WJ - H; a += nw) {
-        int rp = (par0 + a) & 1, j = wj0 + a;
+    W.residual(H - 1, par0);
+    {
+        const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
-            if (b < H || b >= TW - H) continue;
-            if (!(W.B[p] & NB_SELF)) continue;
-            if (j >= L.ny() || wi0 + b >= L.nx()) continue;   // periodic images are another tile's
-            long g = L.index(j, wi0 + b);
-            if (g >= 0) xout[g] = W.X[p];
+        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
+            int a = H + warp + r * TILE_WARPS;
+            if (a >= WJ - H) break;
+            int rp = (par0 + a) & 1, j = wj0 + a;
+            long rb = L.row(j);
+            if (rb < 0) continue;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int b = 2 * k + h, p = W.at(rp ^ h, a, k), ch = h ? c1 : c0;
+                if (b < H || b >= TW - H || ch < 0) continue;
+                if (!(W.B[p] & NB_SELF)) continue;
+                if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
+                xout[rb + ch] = W.X[p];
+            }
         }
     }
     __syncthreads();
@@ -286,7 +344,7 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
 // UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
 // ---------------------------------------------------------------------------
 template <typename T, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 2)
 k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
         const double *__restrict__ scal, int sumr_slot, double inv_n,
         int nyc, int nxc, int pitchc, int periodic_c, const TC *__restrict__ xc,
@@ -297,73 +355,46 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
     extern __shared__ __align__(16) unsigned char smem[];
     Window<T, FINE, WJ> W;
     W.carve(smem);
-    T *XC = reinterpret_cast<T *>(smem + ((Window<T, FINE, WJ>::bytes() + 15) & ~size_t(15)));
+    TC *XC = reinterpret_cast<TC *>(smem + ((Window<T, FINE, WJ>::bytes() + 15) & ~size_t(15)));
     const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
-    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, nw = TILE_THREADS >> 5;
-    const int dirichlet = L.dirichlet();
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     T fshift = T(0);
     if constexpr (FINE) {
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        fill_tables<T>(L.F, W.tab_dinv, W.tab_diag);
+        W.fill_tables(&L.F, L.dirichlet());
         if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
-    }
+    } else W.fill_tables(nullptr, L.dirichlet());
     // ---- coarse window
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
     for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
         int a = t / CI, b = t - a * CI;
         int J = cj0 + a, I = ci0 + b;
-        T v = T(0);
+        TC v = TC(0);
         if (J >= 0 && J < nyc) {
-            if (periodic_c) I = wrap_mod(I, nxc);
-            if (I >= 0 && I < nxc) v = (T)xc[(long)(J + 1) * pitchc + I + 1];
+            if (periodic_c) I = wrap_col(I, nxc);
+            if (I >= 0 && I < nxc) v = xc[(long)(J + 1) * pitchc + I + 1];
         }
         XC[t] = v;
     }
-    // ---- fine window
-    for (int a = warp; a < WJ; a += nw) {
-        int rp = (par0 + a) & 1, j = wj0 + a;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
-            long g = L.index(j, wi0 + b);
-            T fv = T(0), xv = T(0);
-            uint8_t bits = 0;
-            if constexpr (FINE) {
-                if (g >= 0) {
-                    bits = L.F.nb[g];
-                    if (bits & NB_SELF) { fv = (T)fscale * fin[g] - fshift; xv = xin[g]; }
-                }
-            } else {
-                T cxv = T(0), cyv = T(0), div = T(0);
-                if (g >= 0) {
-                    bits = L.A.code[g];
-                    fv = fin[g];
-                    xv = xin[g];
-                    cxv = L.A.cx[g]; cyv = L.A.cy[g]; div = L.A.dinv[g];
-                }
-                W.CX[p] = cxv; W.CY[p] = cyv; W.DI[p] = div;
-            }
-            W.B[p] = bits; W.Fv[p] = fv; W.X[p] = xv;
-        }
-    }
+    W.template load<true>(L, xin, fin, (T)fscale, fshift, wj0, wi0, par0);
     __syncthreads();
     // ---- prolongation on the whole window
-    for (int a = warp; a < WJ; a += nw) {
+#pragma unroll
+    for (int r = 0; r < WJ / TILE_WARPS; r++) {
+        int a = warp + r * TILE_WARPS;
         int rp = (par0 + a) & 1, j = wj0 + a;
         int J0 = (j >> 1) - cj0, Jn = J0 + ((j & 1) ? 1 : -1);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
+            int b = 2 * k + h, p = W.at(rp ^ h, a, k);
             uint8_t bits = W.B[p];
             if (!(bits & NB_SELF)) continue;
             int i = wi0 + b;
             int I0 = (i >> 1) - ci0, In = I0 + ((i & 1) ? 1 : -1);
-            T v = T(9) * XC[J0 * CI + I0] + T(3) * XC[Jn * CI + I0] + T(3) * XC[J0 * CI + In] + XC[Jn * CI + In];
-            T w16 = dirichlet ? T(16) : T(9 + ((bits & NB_PJ) ? 3 : 0) + ((bits & NB_PI) ? 3 : 0) +
-                                          ((bits & NB_PJI) ? 1 : 0));
-            W.X[p] += v / w16;
+            T v = T(9) * (T)XC[J0 * CI + I0] + T(3) * ((T)XC[Jn * CI + I0] + (T)XC[J0 * CI + In]) + (T)XC[Jn * CI + In];
+            W.X[p] += v * W.tab_invw[bits >> 5];
         }
     }
     __syncthreads();
@@ -375,19 +406,25 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
     }
     // ---- write the interior (+ dots)
     double acc[2] = {0.0, 0.0};
-    for (int a = H + warp; a < WJ - H; a += nw) {
-        int rp = (par0 + a) & 1, j = wj0 + a;
+    {
+        const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int b = 2 * k + h, c = rp ^ h, p = W.at(c, a, k);
-            if (b < H || b >= TW - H) continue;
-            if (!(W.B[p] & NB_SELF)) continue;
-            if (j >= L.ny() || wi0 + b >= L.nx()) continue;   // periodic images are another tile's
-            long g = L.index(j, wi0 + b);
-            if (g < 0) continue;
-            T xv = W.X[p];
-            xout[g] = xv;
-            if (DOT) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
+        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
+            int a = H + warp + r * TILE_WARPS;
+            if (a >= WJ - H) break;
+            int rp = (par0 + a) & 1, j = wj0 + a;
+            long rb = L.row(j);
+            if (rb < 0) continue;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int b = 2 * k + h, p = W.at(rp ^ h, a, k), ch = h ? c1 : c0;
+                if (b < H || b >= TW - H || ch < 0) continue;
+                if (!(W.B[p] & NB_SELF)) continue;
+                if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
+                T xv = W.X[p];
+                xout[rb + ch] = xv;
+                if (DOT) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
+            }
         }
     }
     if (DOT) grid_reduce<OpSum, 2>(acc, part, count, out);
