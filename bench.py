@@ -142,6 +142,9 @@ def run_ours(args):
     n = args.n
     p = param_for(n, f2d.Param)
     p.device = local
+    p.solver_nu = args.nu
+    p.solver_rtol = args.rtol
+    p.solver_guess = args.guess
     model = f2d.Model(p)
     mesh, s, eng, integ = model.mesh, model.state, model.mesh.engine, model.integrator
 
@@ -211,15 +214,17 @@ def run_ours(args):
     # ---- roofline of the individual kernels, timed alone on the same stream ---
     peak, peak_src = measured_peak()
     kernels = {}
-    for name in eng.bench_kernel_names():
+    for name in ([] if args.no_kernels else eng.bench_kernel_names()):
         kms, kbytes = eng.bench_kernel(name, 20)
         kernels[name] = {"ms": round(kms, 4), "alg_bytes": kbytes,
                          "gbs": round(kbytes / (kms * 1e-3) / 1e9, 1) if kbytes else None,
                          "frac": round(kbytes / (kms * 1e-3) / 1e9 / peak, 3) if kbytes else None}
     dom = eng.dominant_kernel()
-    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
-            "kernels": kernels}
+    roof = None
+    if kernels:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "kernels": kernels}
 
     out = None
     if rank == 0:
@@ -285,6 +290,10 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=4096, help="grid size (default: the headline 4096)")
     ap.add_argument("--cpu-n", type=int, default=512, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nu", type=int, default=2, help="smoothing sweeps per V-cycle leg")
+    ap.add_argument("--guess", type=int, default=3, help="first-guess extrapolation order (0 off)")
+    ap.add_argument("--rtol", type=float, default=1e-12, help="elliptic solver tolerance")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline timings")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

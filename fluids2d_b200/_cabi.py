@@ -119,7 +119,8 @@ def _noslip_flags(noslip):
     return f
 
 
-def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_kind=0, nu1=0, nu2=0):
+def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_kind=0, nu1=0, nu2=0,
+                      guess_order=None):
     """param.py:13-59 attributes -> f2d_config."""
     if param.model not in MODELS:
         raise NotImplementedError(
@@ -143,6 +144,8 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
     cfg.device = device
     cfg.solver_rtol, cfg.solver_maxit, cfg.solver_kind = solver_rtol, solver_maxit, solver_kind
     cfg.nu1, cfg.nu2 = nu1, nu2
+    if guess_order is not None:
+        cfg.reserved[0] = int(guess_order) + 1
     return cfg
 
 

@@ -58,6 +58,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     F2D_CUDA(cudaSetDevice(cfg->device));
     f2d_ctx *c = new f2d_ctx();
     c->cfg = *cfg;
+    c->guess_order = cfg->reserved[0] > 0 ? cfg->reserved[0] - 1 : 3;   // guess_order + 1 (0 = default)
     c->nh = cfg->nh;
     c->n1 = cfg->nx + 2 * cfg->nh;
     c->n2 = cfg->ny + 2 * cfg->nh;
@@ -125,6 +126,7 @@ int f2d_destroy(f2d_ctx *c) {
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     for (int w = 0; w < 3; w++) mg_free(c, w);
+    for (auto &G : c->guess) for (double *g : G.g) cudaFree(g);
     for (auto &kv : c->mesh) cudaFree(kv.second);
     for (auto &kv : c->fields) cudaFree(kv.second);
     cudaFree(c->hb);
@@ -157,6 +159,7 @@ int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
     NEED(c, "null ctx");
     F2D_CUDA(cudaSetDevice(c->cfg.device));
     F2D_TRY(build_mesh(c, h_msk));
+    for (auto &G : c->guess) G.valid = 0;     // a new mask invalidates the solve history
     // meshes.py:39-47
     F2D_TRY(mg_build(c, F2D_SOLVER_CENTERS));
     F2D_TRY(mg_build(c, F2D_SOLVER_VERTICES));

@@ -87,6 +87,13 @@ struct Multigrid {
 
 }  // namespace f2d
 
+namespace f2d {
+struct GuessHistory {            // last solutions of one RK stage's elliptic solve
+    double *g[3] = {nullptr, nullptr, nullptr};
+    int valid = 0;
+};
+}  // namespace f2d
+
 struct f2d_ctx {
     f2d_config cfg{};
     int n1 = 0, n2 = 0, nh = 0;
@@ -108,6 +115,9 @@ struct f2d_ctx {
     double *tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // work arrays (n2,n1)
 
     f2d::Multigrid mg[3];
+    f2d::GuessHistory guess[3];
+    int guess_order = 3;            // 0 off, 1 previous step, 2 linear, 3 quadratic extrapolation
+    int stage_hint = -1;
     // reductions
     double *d_scal = nullptr;       // device scalars
     double *d_part = nullptr;       // per-block partial sums

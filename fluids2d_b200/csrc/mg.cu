@@ -19,6 +19,8 @@
 //   smoother   red-black Gauss-Seidel, nu1 sweeps (R,B) down, nu2 (B,R) up.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "engine.cuh"
 #include "reduce.cuh"
@@ -724,6 +726,15 @@ int mg_build(f2d_ctx *c, int which) {
     M.tail = (int)M.lev.size() - 1;
     for (int l = (int)M.lev.size() - 1; l >= 1; l--)
         if ((long)M.lev[l].ny * M.lev[l].nx <= 4096 && (int)M.lev.size() - l <= 16) M.tail = l;
+    {   // x, b, r of every tail level must fit in shared memory
+        auto need = [&](int from) {
+            size_t b = 0;
+            for (size_t l = from; l < M.lev.size(); l++) b += (size_t)3 * (M.lev[l].ny + 2) * (M.lev[l].nx + 2) * sizeof(CT);
+            return b;
+        };
+        while (M.tail < (int)M.lev.size() - 1 && need(M.tail) > 200 * 1024) M.tail++;
+        if (need(M.tail) > 200 * 1024) { set_error("coarsest multigrid level too large (%d x %d)", M.lev.back().ny, M.lev.back().nx); return F2D_ERR_UNSUPPORTED; }
+    }
     // coefficients, level by level
     k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0);
     LAUNCH_CHECK(c);
@@ -760,11 +771,15 @@ int mg_build(f2d_ctx *c, int which) {
 
 // ---------------------------------------------------------------------------
 // single-CTA tail: the whole sub-V-cycle of the levels whose grids are small
-// (<= 4096 points) in one launch, arrays in global memory (L1/L2 resident).
+// (<= 4096 points) in one launch.  x, b and the residual of every tail level
+// live in shared memory (the only arrays with write -> read dependencies inside
+// the kernel); the coefficients are read through the read-only path.
 // ---------------------------------------------------------------------------
 struct TailLevel {
-    int ny, nx, pitch;
-    CT *x, *b, *r;
+    int ny, nx, pitch;          // global arrays: (ny+2) x pitch
+    int sp, off;                // shared arrays: pitch nx+2, offset (in CT) of x; b, r follow
+    CT *x;
+    const CT *b;
     const CT *cx, *cy, *dinv;
     const uint8_t *code;
 };
@@ -773,104 +788,119 @@ struct TailArgs {
     TailLevel lev[16];
 };
 
-__device__ __forceinline__ void tail_relax(const TailLevel &L, int periodic, int color, bool zero) {
-    int npts = L.ny * L.nx;
-    for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-        int J = t / L.nx, I = t - J * L.nx;
+#define TAIL_LOOP(L)                                            \
+    for (int J = threadIdx.x >> 5; J < (L).ny; J += 32)         \
+        for (int I = threadIdx.x & 31; I < (L).nx; I += 32)
+
+struct TailSm { CT *x, *b, *r; };
+__device__ __forceinline__ TailSm tail_sm(CT *sm, const TailLevel &L) {
+    int n = (L.ny + 2) * L.sp;
+    return TailSm{sm + L.off, sm + L.off + n, sm + L.off + 2 * n};
+}
+
+__device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const CT *x, int periodic, int J, int I) {
+    long g = (long)(J + 1) * L.pitch + I + 1, ge = g + 1;
+    int s = (J + 1) * L.sp + I + 1, w = s - 1, e = s + 1;
+    if (periodic) {
+        if (I == 0) w = s + (L.nx - 1);
+        if (I == L.nx - 1) { e = s - (L.nx - 1); ge = g - (L.nx - 1); }
+    }
+    return __ldg(L.cx + g) * x[w] + __ldg(L.cx + ge) * x[e] + __ldg(L.cy + g) * x[s - L.sp] +
+           __ldg(L.cy + g + L.pitch) * x[s + L.sp];
+}
+
+__device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
+    TailSm S = tail_sm(sm, L);
+    TAIL_LOOP(L) {
         if (((I + J) & 1) != color) continue;
-        long c = (long)(J + 1) * L.pitch + I + 1, w = c - 1, e = c + 1;
-        if (periodic) { if (I == 0) w = c + (L.nx - 1); if (I == L.nx - 1) e = c - (L.nx - 1); }
-        CT di = L.dinv[c];
-        if (di == CT(0)) continue;
-        CT a = CT(0);
-        if (!zero) a = L.cx[c] * L.x[w] + L.cx[e] * L.x[e] + L.cy[c] * L.x[c - L.pitch] + L.cy[c + L.pitch] * L.x[c + L.pitch];
-        L.x[c] = (L.b[c] + a) * di;
+        CT di = __ldg(L.dinv + (long)(J + 1) * L.pitch + I + 1);
+        int s = (J + 1) * L.sp + I + 1;
+        CT a = zero ? CT(0) : tail_offdiag(L, S.x, periodic, J, I);
+        S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024) k_mg_tail(TailArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CT *sm = reinterpret_cast<CT *>(smem_raw);
     const int per = A.periodic;
+    {   // right-hand side of the first tail level comes from the level above
+        const TailLevel &L = A.lev[0];
+        TailSm S = tail_sm(sm, L);
+        TAIL_LOOP(L) S.b[(J + 1) * L.sp + I + 1] = L.b[(long)(J + 1) * L.pitch + I + 1];
+    }
     for (int l = 0; l < A.nlev - 1; l++) {
         const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
-        int npts = L.ny * L.nx;
-        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-            int J = t / L.nx, I = t - J * L.nx;
-            L.x[(long)(J + 1) * L.pitch + I + 1] = CT(0);
-        }
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
         __syncthreads();
         for (int s = 0; s < A.nu1; s++) {
-            tail_relax(L, per, 0, s == 0);
-            tail_relax(L, per, 1, false);
+            tail_relax(L, sm, per, 0, s == 0);
+            tail_relax(L, sm, per, 1, false);
         }
-        // residual / W16
-        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-            int J = t / L.nx, I = t - J * L.nx;
-            long c = (long)(J + 1) * L.pitch + I + 1, w = c - 1, e = c + 1;
-            if (per) { if (I == 0) w = c + (L.nx - 1); if (I == L.nx - 1) e = c - (L.nx - 1); }
-            CT di = L.dinv[c], res = CT(0);
+        TAIL_LOOP(L) {   // residual / prolongation normaliser
+            long g = (long)(J + 1) * L.pitch + I + 1;
+            int sidx = (J + 1) * L.sp + I + 1;
+            CT di = __ldg(L.dinv + g), res = CT(0);
             if (di != CT(0)) {
-                CT a = L.cx[c] * L.x[w] + L.cx[e] * L.x[e] + L.cy[c] * L.x[c - L.pitch] + L.cy[c + L.pitch] * L.x[c + L.pitch];
-                res = (L.b[c] - (L.x[c] / di - a)) / (CT)w16_of(L.code[c], A.dirichlet);
+                CT a = tail_offdiag(L, S.x, per, J, I);
+                res = (S.b[sidx] - (S.x[sidx] / di - a)) / (CT)w16_of(__ldg(L.code + g), A.dirichlet);
             }
-            L.r[c] = res;
+            S.r[sidx] = res;
         }
         __syncthreads();
-        // restriction
-        int nc = C.ny * C.nx;
-        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
-            int J = t / C.nx, I = t - J * C.nx;
+        TAIL_LOOP(C) {   // restriction R = P^T
             CT acc = CT(0);
+#pragma unroll
             for (int a = -1; a <= 2; a++) {
                 int j = 2 * J + a;
                 if (j < 0 || j >= L.ny) continue;
                 CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
+#pragma unroll
                 for (int b = -1; b <= 2; b++) {
                     int i = 2 * I + b;
                     if (per) i = wrap_mod(i, L.nx);
                     else if (i < 0 || i >= L.nx) continue;
                     CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
-                    acc += wy * wx * L.r[(long)(j + 1) * L.pitch + i + 1];
+                    acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
                 }
             }
-            C.b[(long)(J + 1) * C.pitch + I + 1] = acc;
+            SC.b[(J + 1) * C.sp + I + 1] = acc;
         }
         __syncthreads();
     }
     {   // coarsest: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
         const TailLevel &L = A.lev[A.nlev - 1];
-        int npts = L.ny * L.nx;
-        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-            int J = t / L.nx, I = t - J * L.nx;
-            L.x[(long)(J + 1) * L.pitch + I + 1] = CT(0);
-        }
+        TailSm S = tail_sm(sm, L);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
         __syncthreads();
         for (int s = 0; s < 4 * A.nsw; s++)
-            tail_relax(L, per, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
+            tail_relax(L, sm, per, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
     }
     for (int l = A.nlev - 2; l >= 0; l--) {
         const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
-        int npts = L.ny * L.nx;
-        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-            int j = t / L.nx, i = t - j * L.nx;
-            long idx = (long)(j + 1) * L.pitch + i + 1;
-            uint8_t c = L.code[idx];
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        TAIL_LOOP(L) {
+            uint8_t c = __ldg(L.code + (long)(J + 1) * L.pitch + I + 1);
             if (!(c & NB_SELF)) continue;
             int J0, Jn, I0, In;
-            parents(j, i, J0, Jn, I0, In);
+            parents(J, I, J0, Jn, I0, In);
             if (per) In = wrap_mod(In, C.nx);
-            long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;
-            CT v = CT(9) * C.x[r0 + I0 + 1];
-            if (c & NB_PJ) v += CT(3) * C.x[rn + I0 + 1];
-            if (c & NB_PI) v += CT(3) * C.x[r0 + In + 1];
-            if (c & NB_PJI) v += C.x[rn + In + 1];
-            L.x[idx] += v / (CT)w16_of(c, A.dirichlet);
+            int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
+            CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
+            S.x[(J + 1) * L.sp + I + 1] += v / (CT)w16_of(c, A.dirichlet);
         }
         __syncthreads();
         for (int s = 0; s < A.nu2; s++) {
-            tail_relax(L, per, 1, false);
-            tail_relax(L, per, 0, false);
+            tail_relax(L, sm, per, 1, false);
+            tail_relax(L, sm, per, 0, false);
         }
+    }
+    {   // the correction of the first tail level goes back to global memory
+        const TailLevel &L = A.lev[0];
+        TailSm S = tail_sm(sm, L);
+        TAIL_LOOP(L) L.x[(long)(J + 1) * L.pitch + I + 1] = S.x[(J + 1) * L.sp + I + 1];
     }
 }
 
@@ -988,11 +1018,17 @@ static int launch_tail(f2d_ctx *c, Multigrid &M) {
     A.nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
     const Level &last = M.lev[nlev - 1];
     A.nsw = last.ny * last.nx <= 64 ? 8 : 24;
+    int off = 0;
     for (int l = M.tail; l < nlev; l++) {
         const Level &L = M.lev[l];
-        A.lev[l - M.tail] = TailLevel{L.ny, L.nx, L.pitch, L.x, L.b, L.r, L.cx, L.cy, L.dinv, L.code};
+        int sp = L.nx + 2;
+        A.lev[l - M.tail] = TailLevel{L.ny, L.nx, L.pitch, sp, off, L.x, L.b, L.cx, L.cy, L.dinv, L.code};
+        off += 3 * (L.ny + 2) * sp;
     }
-    k_mg_tail<<<1, 1024, 0, c->stream>>>(A);
+    size_t smem = (size_t)off * sizeof(CT);
+    static size_t configured = 0;
+    if (smem > configured) { F2D_TRY(set_smem(k_mg_tail, smem)); configured = smem; }
+    k_mg_tail<<<1, 1024, smem, c->stream>>>(A);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -1153,6 +1189,8 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             if (!(relres > rtol)) conv = true;
         }
         double best = relres;
+        static const bool debug = getenv("F2D_DEBUG") != nullptr;
+        if (debug) fprintf(stderr, "[f2d] solve %d: initial relres %.3e\n", which, relres);
         double *pold = M.p, *pnew = M.p2;
         const int slot = singular ? S_SUMR : -1;   // lazy projection r - mean(r)
         for (it = 0; !conv && it < maxit; it++) {
@@ -1172,6 +1210,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             std::swap(pold, pnew);
             F2D_TRY(read_scalars(c, S_RR, 2));
             relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
+            if (debug) fprintf(stderr, "[f2d]   it %d relres %.3e\n", it + 1, relres);
             if (!(relres > rtol)) { conv = true; it++; break; }
             best = std::min(best, relres);
             if (!(relres < 1e6 * best)) { it++; break; }   // diverging: give up, report

@@ -6,6 +6,8 @@
 // evaluating halo columns at their periodic image column.  Index arithmetic
 // is the reference's flat-index arithmetic (weno.py:346-405), guarded by the
 // same stencil-order arrays, so interior results depend on the same operands.
+#include <algorithm>
+
 #include "engine.cuh"
 #include "reduce.cuh"
 #include "weno.cuh"
@@ -53,14 +55,24 @@ enum { M_EULER = 0, M_BOUSS = 1, M_RSW = 2, M_QGRSW = 3 };
 //   + addcoriolis (:32-39) + addgrad(ke) / addgrad(p) (:49-53) + addbuoyancy
 //   (:152-153), then fill.          equations.py:11-15, 29-35, 121-127, 141-148
 // ---------------------------------------------------------------------------
-template <int MV, int MODEL>
+// NC > 0 fuses the Runge-Kutta update of the velocity (integrators.py:154-174):
+//   ub = u + ((c0 ds_0) + c1 ds_1) + c2 ds_2, the last ds being this tendency;
+//   ub is a second buffer because neighbouring threads still read u.
+struct RkFuse {
+    double c[3];
+    const double *dx[2], *dy[2];   // earlier tendencies
+    double *ubx, *uby;             // updated velocity
+    int write_ds;                  // later stages need this tendency
+};
+
+template <int MV, int MODEL, int NC>
 __global__ void __launch_bounds__(256)
 k_rhs_mom(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
           const double *__restrict__ omega, const double *__restrict__ ke,
           const double *__restrict__ p, const double *__restrict__ b,
           const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy,
           const int8_t *__restrict__ mskx, const int8_t *__restrict__ msky,
-          double fcor, double halfdy, double *__restrict__ dux, double *__restrict__ duy) {
+          double fcor, double halfdy, double *__restrict__ dux, double *__restrict__ duy, RkFuse rk) {
     THREAD_2D(g);
     double rx = 0, ry = 0;
     int oy = ovy[k];
@@ -100,8 +112,24 @@ k_rhs_mom(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
     if (MODEL == M_BOUSS) {
         if (j >= 1) ry += (halfdy * (b[k] + b[k - s1])) * (double)msky[k];
     }
-    dux[k_out] = rx;
-    duy[k_out] = ry;
+    if (NC == 0 || rk.write_ds) {
+        dux[k_out] = rx;
+        duy[k_out] = ry;
+    }
+    if (NC > 0) {
+        double ax, ay;
+        if (NC == 1) { ax = rk.c[0] * rx; ay = rk.c[0] * ry; }
+        else {
+            ax = rk.c[0] * rk.dx[0][k_out]; ay = rk.c[0] * rk.dy[0][k_out];
+            if (NC == 2) { ax = ax + rk.c[1] * rx; ay = ay + rk.c[1] * ry; }
+            else {
+                ax = ax + rk.c[1] * rk.dx[1][k_out]; ay = ay + rk.c[1] * rk.dy[1][k_out];
+                ax = ax + rk.c[2] * rx; ay = ay + rk.c[2] * ry;
+            }
+        }
+        rk.ubx[k_out] = ux[k_out] + ax;
+        rk.uby[k_out] = uy[k_out] + ay;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -322,8 +350,8 @@ k_maxabs(long n, const double *__restrict__ ux, const double *__restrict__ uy, d
         F2D_CUDA(cudaGetLastError());   \
     } while (0)
 
-template <int MODEL>
-static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy) {
+template <int MODEL, int NC = 0>
+static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy, RkFuse rk = RkFuse()) {
     Grid g = grid_of(c);
     const double *p = c->has("p") ? c->f("p") : nullptr;
     const double *b = c->has("b") ? c->f("b") : nullptr;
@@ -331,12 +359,12 @@ static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy) {
     double fcor = c->cfg.f0 * c->area * 0.25;
     double halfdy = 0.5 * c->dy;
 #define RHS_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), ke, p, b, c->m("ov.x"), c->m("ov.y"), \
-                 c->m("mskx"), c->m("msky"), fcor, halfdy, dux, duy
+                 c->m("mskx"), c->m("msky"), fcor, halfdy, dux, duy, rk
     switch (c->cfg.vortexforce) {
-    case F2D_METHOD_WENO: k_rhs_mom<WENO, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
-    case F2D_METHOD_UPWIND: k_rhs_mom<UPWIND, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
-    case F2D_METHOD_CENTERED: k_rhs_mom<CENTERED, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
-    case F2D_METHOD_CWENO: k_rhs_mom<CWENO, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_WENO: k_rhs_mom<WENO, MODEL, NC><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_UPWIND: k_rhs_mom<UPWIND, MODEL, NC><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_CENTERED: k_rhs_mom<CENTERED, MODEL, NC><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
+    case F2D_METHOD_CWENO: k_rhs_mom<CWENO, MODEL, NC><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
     default: set_error("bad vortexforce method"); return F2D_ERR_ARG;
     }
 #undef RHS_ARGS
@@ -359,6 +387,52 @@ static int launch_divflux(f2d_ctx *c, const double *q, double *dq) {
     LAUNCH_CHECK(c);
     k_divflux<<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dq);
     LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+// ---------------------------------------------------------------------------
+// First guess of the elliptic solves inside f2d_step.  The reference's direct
+// solve ignores what x holds; an iterative solve does not.  The solution of RK
+// stage k changes slowly from one time step to the next, while it differs by
+// O(1) between stages (the incremental RK form scales each stage's pressure by
+// other coefficients) -- so the guess is extrapolated from the SAME stage of the
+// previous steps: x0 = 2 g1 - g2 (or g1, or what x holds, as history allows).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_guess(long n, double *__restrict__ x, const double *__restrict__ g1, const double *__restrict__ g2,
+        const double *__restrict__ g3, int order) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (order == 1) x[k] = g1[k];
+    else if (order == 2) x[k] = 2.0 * g1[k] - g2[k];
+    else x[k] = 3.0 * (g1[k] - g2[k]) + g3[k];
+}
+
+static int guess_before(f2d_ctx *c, int stage, double *x) {
+    if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
+    GuessHistory &G = c->guess[stage];
+    int order = std::min(G.valid, c->guess_order);
+    if (order <= 0) return F2D_OK;
+    long n = (long)c->n;
+    k_guess<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, x, G.g[0], G.g[1], G.g[2], order);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+static int guess_after(f2d_ctx *c, int stage, const double *x) {
+    if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
+    GuessHistory &G = c->guess[stage];
+    for (int k = 0; k < std::min(c->guess_order, 3); k++)
+        if (!G.g[k]) {
+            F2D_CUDA(cudaMalloc(&G.g[k], c->n * sizeof(double)));
+            F2D_CUDA(cudaMemsetAsync(G.g[k], 0, c->n * sizeof(double), c->stream));
+        }
+    // rotate: g3 <- g2 <- g1 <- x
+    double *last = G.g[std::min(c->guess_order, 3) - 1];
+    for (int k = std::min(c->guess_order, 3) - 1; k > 0; k--) G.g[k] = G.g[k - 1];
+    G.g[0] = last;
+    F2D_CUDA(cudaMemcpyAsync(G.g[0], x, c->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    G.valid = std::min(G.valid + 1, 3);
     return F2D_OK;
 }
 
@@ -387,7 +461,9 @@ int model_rhs(f2d_ctx *c, int k) {
         k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, dux, duy, dh, c->m("slip"), c->m("mskv"),
                                                       mf0H, c->f("pv"));
         LAUNCH_CHECK(c);
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi")));
         F2D_TRY(mg_solve(c, F2D_SOLVER_HELMHOLTZ, c->f("pv"), 1.0, c->f("psi"), nullptr, nullptr));
+        F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
         double f0ag = c->cfg.f0 * c->area / c->cfg.g;
         k_qg_back<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("msk"), c->m("mskx"),
                                                         c->m("msky"), c->m("mskv"), f0ag, dux, duy, dh);
@@ -440,22 +516,27 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
     return F2D_OK;
 }
 
-int model_diag(f2d_ctx *c) {
+// `pre`: the un-projected velocity already sits in tmp[0..1] (fused stage kernel)
+static int model_diag_impl(f2d_ctx *c, bool pre) {
     if (!c->mesh_ready) { set_error("f2d_diag before f2d_set_mask"); return F2D_ERR_STATE; }
     Grid g = grid_of(c);
     switch (c->cfg.model) {
     case F2D_MODEL_EULER:
     case F2D_MODEL_BOUSSINESQ: {
         double *ux = c->f("u.x"), *uy = c->f("u.y");
-        k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, ux, uy, c->m("msk"), c->f("div"));
+        if (!pre) {
+            // the projection reads neighbours of u, so it cannot run in place:
+            // copy the un-projected velocity aside first
+            size_t bytes = c->n * sizeof(double);
+            F2D_CUDA(cudaMemcpyAsync(c->tmp[0], ux, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            F2D_CUDA(cudaMemcpyAsync(c->tmp[1], uy, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->tmp[0], c->tmp[1], c->m("msk"), c->f("div"));
         LAUNCH_CHECK(c);
         // A p = -delta * area       (operators.py:117)
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("p")));
         F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
-        // the projection reads neighbours of u, so it cannot run in place:
-        // copy the un-projected velocity aside first
-        size_t bytes = c->n * sizeof(double);
-        F2D_CUDA(cudaMemcpyAsync(c->tmp[0], ux, bytes, cudaMemcpyDeviceToDevice, c->stream));
-        F2D_CUDA(cudaMemcpyAsync(c->tmp[1], uy, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        F2D_TRY(guess_after(c, c->stage_hint, c->f("p")));
         return launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct);
     }
     case F2D_MODEL_RSW:
@@ -466,6 +547,8 @@ int model_diag(f2d_ctx *c) {
     set_error("unknown model %d", c->cfg.model);
     return F2D_ERR_ARG;
 }
+
+int model_diag(f2d_ctx *c) { return model_diag_impl(c, false); }
 
 // integrators.py:82-124, incremental form
 static int rk_coefs(int integ, double dt, int stage, double *co) {
@@ -483,15 +566,58 @@ static int rk_coefs(int integ, double dt, int stage, double *co) {
     return 0;
 }
 
+// Euler / Boussinesq stage with the velocity update fused into the tendency
+// kernel: u* = u + sum c_i ds_i lands in tmp[0..1], the projection writes u.
+static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
+    RkFuse rk;
+    for (int k = 0; k < 3; k++) rk.c[k] = k < nc ? co[k] : 0.0;
+    for (int k = 0; k < 2; k++) {
+        rk.dx[k] = k < nc - 1 ? c->f(dsname(k, "u.x")) : nullptr;
+        rk.dy[k] = k < nc - 1 ? c->f(dsname(k, "u.y")) : nullptr;
+    }
+    rk.ubx = c->tmp[0]; rk.uby = c->tmp[1];
+    rk.write_ds = s < c->nstages - 1;
+    double *dux = c->f(dsname(s, "u.x")), *duy = c->f(dsname(s, "u.y"));
+    const bool bouss = c->cfg.model == F2D_MODEL_BOUSSINESQ;
+#define STAGE(NCV)                                                                     \
+    (bouss ? launch_rhs_mom<M_BOUSS, NCV>(c, dux, duy, rk) : launch_rhs_mom<M_EULER, NCV>(c, dux, duy, rk))
+    if (nc == 1) F2D_TRY(STAGE(1));
+    else if (nc == 2) F2D_TRY(STAGE(2));
+    else F2D_TRY(STAGE(3));
+#undef STAGE
+    if (bouss) {
+        // buoyancy: tendency from the old b (the momentum kernel above has read it), then update
+        F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
+        long n = (long)c->n;
+        unsigned grd = (unsigned)((n + 255) / 256);
+        double *y = c->f("b");
+        const double *x0 = c->f(dsname(0, "b")), *x1 = nc > 1 ? c->f(dsname(1, "b")) : nullptr,
+                     *x2 = nc > 2 ? c->f(dsname(2, "b")) : nullptr;
+        if (nc == 1) k_addto<1><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], 0, 0);
+        else if (nc == 2) k_addto<2><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], 0);
+        else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], co[2]);
+        LAUNCH_CHECK(c);
+    }
+    return model_diag_impl(c, true);
+}
+
 int model_step(f2d_ctx *c, double dt, int nsteps) {
     if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
     for (int it = 0; it < nsteps; it++) {
         for (int s = 0; s < c->nstages; s++) {
             double co[3];
             int nc = rk_coefs(c->cfg.integrator, dt, s, co);
-            F2D_TRY(model_rhs(c, s));
-            F2D_TRY(model_addto(c, nc, co));
-            F2D_TRY(model_diag(c));
+            c->stage_hint = s;      // the solves of this stage may use its history
+            int st;
+            if (c->cfg.model == F2D_MODEL_EULER || c->cfg.model == F2D_MODEL_BOUSSINESQ)
+                st = fused_stage(c, s, nc, co);
+            else {
+                st = model_rhs(c, s);
+                if (st == F2D_OK) st = model_addto(c, nc, co);
+                if (st == F2D_OK) st = model_diag(c);
+            }
+            c->stage_hint = -1;
+            F2D_TRY(st);
         }
     }
     return F2D_OK;
@@ -533,9 +659,14 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < n; r++) {
             if (k == "advection") {
-                // R u.x u.y omega ke, W ds.x ds.y, masks ov.x ov.y mskx msky
-                F2D_TRY(launch_rhs_mom<M_EULER>(c, c->f("ds0.u.x"), c->f("ds0.u.y")));
-                *bytes = npts * (6 * 8 + 4);
+                // stage 2 of rk3, fused with the RK update:
+                // R u.x u.y omega ke ds0.x ds0.y, W ds1.x ds1.y ub.x ub.y, masks ov.x ov.y mskx msky
+                RkFuse rk;
+                rk.c[0] = rk.c[1] = rk.c[2] = 0.0;
+                rk.dx[0] = c->f("ds0.u.x"); rk.dy[0] = c->f("ds0.u.y"); rk.dx[1] = rk.dy[1] = nullptr;
+                rk.ubx = c->tmp[0]; rk.uby = c->tmp[1]; rk.write_ds = 1;
+                F2D_TRY((launch_rhs_mom<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
+                *bytes = npts * (10 * 8 + 4);
             } else if (k == "rk_update") {
                 // R u ds0 ds1 ds2, W u (one component; coefficients 0 keep u intact)
                 long n1 = (long)c->n;

@@ -30,7 +30,9 @@ class Mesh:
         kind = {"pcg": 0, "mg": 1}[getattr(param, "solver", "pcg")]
         self.engine = Engine(param, device=getattr(param, "device", 0),
                              solver_rtol=getattr(param, "solver_rtol", 0.0),
-                             solver_maxit=getattr(param, "solver_maxit", 0), solver_kind=kind)
+                             solver_maxit=getattr(param, "solver_maxit", 0), solver_kind=kind,
+                             nu1=getattr(param, "solver_nu", 0), nu2=getattr(param, "solver_nu", 0),
+                             guess_order=getattr(param, "solver_guess", None))
         self._hb = 0
         self.set_default_mask()
         self.finalize()

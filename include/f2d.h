@@ -67,7 +67,9 @@ typedef struct {
     int32_t solver_maxit;   /* 0 -> 100                                      */
     int32_t solver_kind;    /* 0 MG-preconditioned CG, 1 plain V-cycles      */
     int32_t nu1, nu2;       /* red-black sweeps before / after; 0 -> 2       */
-    int32_t reserved[8];
+    int32_t reserved[8];    /* [0]: 1 + order of the first-guess extrapolation across
+                             * time steps for the solves inside f2d_step (0 = default
+                             * = quadratic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic) */
 } f2d_config;
 
 int f2d_version(void);

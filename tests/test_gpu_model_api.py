@@ -108,8 +108,9 @@ def test_multi_step_resident_equals_single_steps(f2d):
 
 def test_forcing_callback_sees_host_state(f2d):
     """model.add_forcing (model.py:121-123): the callback mutates ds on the host
-    every stage; a zero forcing must reproduce the unforced run bit for bit,
-    a non-zero one must change it."""
+    every stage; a zero forcing must reproduce the unforced run (to solver
+    tolerance: the stage-by-stage path has no first-guess history), a non-zero
+    one must change it."""
     g = Golden("warm_bubble")
     def fresh():
         p = f2d.Param()
@@ -132,8 +133,8 @@ def test_forcing_callback_sees_host_state(f2d):
         m.set_dt()
         m.step(2)
     assert len(calls) == 6 and calls[0] > 0
-    assert np.array_equal(a.state.b, b.state.b) and np.array_equal(a.state.u.x, b.state.u.x)
-    assert not np.array_equal(a.state.b, c.state.b)
+    assert rel_l2(b.state.b, a.state.b) < 1e-11 and rel_l2(b.state.u.x, a.state.u.x) < 1e-10
+    assert rel_l2(c.state.b, a.state.b) > 1e-6
 
 
 def test_integrator_callables_and_scratch(f2d):
