@@ -821,8 +821,14 @@ __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int perio
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k_mg_tail(TailArgs A) {
+__global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailArgs Ain) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // level descriptors are indexed dynamically: keep them in shared memory, not
+    // in a local-memory copy of the parameter block
+    __shared__ TailArgs A;
+    for (int t = threadIdx.x; t < (int)(sizeof(TailArgs) / sizeof(int)); t += blockDim.x)
+        reinterpret_cast<int *>(&A)[t] = reinterpret_cast<const int *>(&Ain)[t];
+    __syncthreads();
     CT *sm = reinterpret_cast<CT *>(smem_raw);
     const int per = A.periodic;
     {   // right-hand side of the first tail level comes from the level above

@@ -176,7 +176,8 @@ def test_granular_calls_equal_fused_step():
         b.addto(co[k])
         b.diag()
     for f in ("u.x", "u.y", "omega", "ke", "p"):
-        assert np.array_equal(a.download(f), b.download(f)), f
+        x, y = a.download(f), b.download(f)
+        assert np.abs(x - y).max() <= 1e-12 * np.abs(y).max(), f   # FMA contraction differs between the fused and the stand-alone update
 
 
 def test_cfl_reduction_matches_numpy():
