@@ -81,6 +81,10 @@ SIGNATURES = {
     "f2d_timer_start": (_I, [_P]),
     "f2d_timer_stop": (_I, [_P, C.POINTER(C.c_float)]),
     "f2d_bench_kernel": (_I, [_P, C.c_char_p, _I, C.POINTER(C.c_float), C.POINTER(_D)]),
+    "f2d_dist_unique_id": (_I, [C.c_char_p]),
+    "f2d_dist_init": (_I, [_P, _I, _I, C.c_char_p]),
+    "f2d_dist_exchange": (_I, [_P, C.c_char_p]),
+    "f2d_exchange_count": (_I, [_P, C.POINTER(_I64)]),
     "f2d_launch_count": (_I, [_P, C.POINTER(_I64)]),
 }
 
@@ -120,7 +124,7 @@ def _noslip_flags(noslip):
 
 
 def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_kind=0, nu1=0, nu2=0,
-                      guess_order=None):
+                      guess_order=None, slab=None):
     """param.py:13-59 attributes -> f2d_config."""
     if param.model not in MODELS:
         raise NotImplementedError(
@@ -132,9 +136,18 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
     cfg = Config()
     cfg.model = MODELS[param.model]
     cfg.nx, cfg.ny, cfg.nh = param.nx, param.ny, param.halowidth
+    if slab is not None and slab.nranks > 1:
+        # the context sees the local slab; dy stays Ly / (global ny)
+        cfg.ny = slab.ny_ctx
+        cfg.reserved[1], cfg.reserved[2], cfg.reserved[3] = slab.gs, slab.gn, slab.ny
     cfg.Lx, cfg.Ly = param.Lx, param.Ly
     cfg.xperiodic, cfg.yperiodic = int(bool(param.xperiodic)), int(bool(param.yperiodic))
     cfg.noslip = _noslip_flags(param.noslip)
+    if slab is not None and slab.nranks > 1 and not (cfg.noslip & NOSLIP_ALL):
+        if slab.rank > 0:
+            cfg.noslip &= ~NOSLIP["bottom"]
+        if slab.rank < slab.nranks - 1:
+            cfg.noslip &= ~NOSLIP["top"]
     cfg.f0, cfg.g, cfg.H = param.f0, param.g, param.H
     cfg.integrator = INTEGRATORS[param.integrator]
     cfg.compflux = METHODS[param.compflux]
@@ -152,14 +165,21 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
 class Engine:
     """One f2d_ctx: device-resident mesh + state + solvers for one Model."""
 
-    def __init__(self, param, device=0, exact=False, **solver_kw):
+    def __init__(self, param, device=0, exact=False, slab=None, comm=None, **solver_kw):
         self.lib = load(exact)
-        self.cfg = config_from_param(param, device=device, **solver_kw)
-        self.shape = (param.ny + 2 * param.halowidth, param.nx + 2 * param.halowidth)
+        self.slab = slab if (slab is not None and slab.nranks > 1) else None
+        self.cfg = config_from_param(param, device=device, slab=self.slab, **solver_kw)
+        self.shape = (self.cfg.ny + 2 * param.halowidth, param.nx + 2 * param.halowidth)
         self.size = self.shape[0] * self.shape[1]
         self._h = C.c_void_p()
         self._chk(self.lib.f2d_create(C.byref(self.cfg), C.byref(self._h)))
         self._dev_allocs = []
+        if self.slab is not None:
+            if comm is None:
+                raise F2DError(-2, "a slab engine needs the NCCL identity (slabs.set_communicator)")
+            rank, world, uid = comm
+            assert (rank, world) == (self.slab.rank, self.slab.nranks)
+            self._chk(self.lib.f2d_dist_init(self._h, rank, world, uid))
 
     # -- errors -------------------------------------------------------------
     def _chk(self, status):
@@ -208,11 +228,16 @@ class Engine:
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert a.shape == self.shape, (name, a.shape, self.shape)
         self._chk(self.lib.f2d_upload(self._h, name.encode(), _ptr(a)))
+        if self.slab is not None and not name.startswith("ds"):
+            self._chk(self.lib.f2d_dist_exchange(self._h, name.encode()))
         self.sync()     # `a` may be a temporary
 
     def upload_async(self, name, a):
         assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == self.shape
         self._chk(self.lib.f2d_upload(self._h, name.encode(), _ptr(a)))
+        if self.slab is not None and not name.startswith("ds"):
+            # host ghost rows may be stale: take them from their owners
+            self._chk(self.lib.f2d_dist_exchange(self._h, name.encode()))
 
     def download(self, name, out=None):
         if out is None:
@@ -368,6 +393,21 @@ class Engine:
         n = C.c_int64()
         self._chk(self.lib.f2d_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def exchange_count(self):
+        n = C.c_int64()
+        self._chk(self.lib.f2d_exchange_count(self._h, C.byref(n)))
+        return n.value
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (call on one rank, hand it to the others)"""
+    lib = load()
+    buf = C.create_string_buffer(128)
+    st = lib.f2d_dist_unique_id(buf)
+    if st != 0:
+        raise F2DError(st, lib.f2d_last_error().decode())
+    return buf.raw
 
 
 def pinned_empty(shape, dtype=np.float64, exact=False):

@@ -13,8 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "ops.cu", "step.cu", "mg.cu"]
-HEADERS = ["engine.cuh", "weno.cuh", "reduce.cuh", os.path.join("..", "..", "include", "f2d.h")]
+SOURCES = ["api.cu", "ops.cu", "step.cu", "mg.cu", "dist.cu"]
+HEADERS = ["engine.cuh", "weno.cuh", "reduce.cuh", "mg_tiles.cuh", os.path.join("..", "..", "include", "f2d.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -41,7 +41,7 @@ def build_one(exact=False, force=False, verbose=False):
         cmd += ["-fmad=false", "-DF2D_EXACT"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
     subprocess.check_call(cmd)
     return out
 

@@ -64,7 +64,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     c->n2 = cfg->ny + 2 * cfg->nh;
     c->n = (size_t)c->n1 * c->n2;
     c->dx = cfg->Lx / cfg->nx;       // meshes.py:24-26
-    c->dy = cfg->Ly / cfg->ny;
+    c->dy = cfg->Ly / (cfg->reserved[3] > 0 ? cfg->reserved[3] : cfg->ny);   // slab: global ny
     c->area = c->dx * c->dy;
     c->idx2 = 1 / (c->dx * c->dx);   // operators.py:61-62
     c->idy2 = 1 / (c->dy * c->dy);
@@ -126,6 +126,7 @@ int f2d_destroy(f2d_ctx *c) {
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     for (int w = 0; w < 3; w++) mg_free(c, w);
+    dist_free(c);
     for (auto &G : c->guess) for (double *g : G.g) cudaFree(g);
     for (auto &kv : c->mesh) cudaFree(kv.second);
     for (auto &kv : c->fields) cudaFree(kv.second);
@@ -321,6 +322,25 @@ int f2d_bench_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *
     NEED(c && name && ms && alg_bytes && reps > 0, "bad argument");
     if (!strncmp(name, "mg.", 3) || !strncmp(name, "cg.", 3)) return bench_mg_kernel(c, name, reps, ms, alg_bytes);
     return bench_step_kernel(c, name, reps, ms, alg_bytes);
+}
+int f2d_dist_unique_id(char *id128) {
+    NEED(id128, "null argument");
+    return dist_unique_id(id128);
+}
+int f2d_dist_init(f2d_ctx *c, int rank, int world, const char *id128) {
+    NEED(c && id128, "null argument");
+    NEED(!c->mesh_ready, "f2d_dist_init must precede f2d_set_mask");
+    return dist_init(c, rank, world, id128);
+}
+int f2d_dist_exchange(f2d_ctx *c, const char *field) {
+    double *p;
+    F2D_TRY(find_field(c, field, &p));
+    return dist_exchange1(c, p, (size_t)c->n1 * sizeof(double), c->n2, 0);
+}
+int f2d_exchange_count(f2d_ctx *c, int64_t *count) {
+    NEED(c && count, "null argument");
+    *count = c->exchanges;
+    return F2D_OK;
 }
 int f2d_launch_count(f2d_ctx *c, int64_t *count) {
     NEED(c && count, "null argument");

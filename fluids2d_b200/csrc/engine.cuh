@@ -1,8 +1,10 @@
 // Internal structures shared by the translation units of libf2d.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,6 +53,8 @@ struct FineView {
     double cx, cy;     // dy/dx, dx/dy   (elliptic.py:138-139)
     double shift;      // maindiag       (elliptic.py:186-190)
     const uint8_t *nb;
+    int jo0, jo1;      // rows this rank owns (reductions); [0, ny) on one GPU
+    int pj_off;        // parent row of fine row j is (j >> 1) + pj_off (ghost rows south)
 };
 
 // Coarse level l >= 1: halo-padded arrays (ny+2) x pitch, element (J,I) at
@@ -59,6 +63,7 @@ struct CoarseView {
     int ny, nx, pitch;
     int periodic;
     int dirichlet;
+    int pj_off;
     const CT *cx;         // coupling across the west face of (J,I)
     const CT *cy;         // coupling across the south face
     const CT *dinv;       // 1/diagonal, 0 where not an unknown
@@ -74,12 +79,30 @@ struct Level {
     uint8_t *code = nullptr;
 };
 
+// y-slab decomposition: one context per GPU/process.  Every array of a rank
+// carries G ghost rows at each interface with a neighbour (at every multigrid
+// level); a kernel's results are exact on the owned rows as long as its domain
+// of dependence is <= G rows, and the ghosts are refreshed from the owners
+// after each kernel (dist.cu).
+struct Dist {
+    bool on = false;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int G = 8;                       // ghost rows at an interface
+    bool south = false, north = false;
+};
+
 struct Multigrid {
     bool built = false;
     int which = 0;
     FineView fine{};
     uint8_t *nb = nullptr;            // fine bits, (n2,n1)
     std::vector<Level> lev;           // lev[0] unused except sizes; lev[l>=1] coarse
+    std::vector<Level> glev;          // slab mode: global (replicated) copies of the tail levels
+    int gs = 0, gn = 0;               // ghost rows south / north of the owned rows, every level
+    int jo0 = 0, jo1 = 0;             // owned logical rows of the fine level [jo0, jo1)
+    int tail_y0 = 0;                  // slab mode: first owned row of level `tail` in the global tail grid
+    double n_global = 0;              // unknowns over all ranks
     double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr, *z2 = nullptr;   // CG vectors (n2,n1)
     int tail = 1;                     // first level handled by the single-CTA tail kernel
     int64_t nunknown = 0;
@@ -101,7 +124,7 @@ struct f2d_ctx {
     double dx = 0, dy = 0, area = 0, idx2 = 0, idy2 = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int64_t launches = 0;
+    int64_t launches = 0, exchanges = 0;
     int nsm = 148;
 
     // mesh (int8, (n2,n1))
@@ -115,6 +138,7 @@ struct f2d_ctx {
     double *tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // work arrays (n2,n1)
 
     f2d::Multigrid mg[3];
+    f2d::Dist dist;
     f2d::GuessHistory guess[3];
     int guess_order = 3;            // 0 off, 1 previous step, 2 linear, 3 quadratic extrapolation
     int stage_hint = -1;
@@ -149,6 +173,14 @@ void mg_free(f2d_ctx *c, int which);
 int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters,
              double *relres);
 int mg_apply(f2d_ctx *c, int which, const double *x, double *y);
+// dist.cu
+int dist_exchange(f2d_ctx *c, int narr, void *const *base, size_t row_bytes, long nrows, long row0);
+int dist_exchange1(f2d_ctx *c, void *base, size_t row_bytes, long nrows, long row0);
+int dist_allreduce(f2d_ctx *c, double *d_vals, int n, bool max_op);
+int dist_allgather_rows(f2d_ctx *c, const void *src_rows, void *dst, size_t bytes_per_rank);
+int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id);
+int dist_unique_id(char *out);
+void dist_free(f2d_ctx *c);
 int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
 int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
 }  // namespace f2d

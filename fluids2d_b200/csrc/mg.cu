@@ -104,8 +104,8 @@ __device__ __forceinline__ void coarse_idx(const CoarseView &V, int J, int I, lo
 
 // parents of a fine cell (logical j,i): own aggregate (J0,I0) and the next
 // nearest in each direction; returns false for a parent outside the grid
-__device__ __forceinline__ void parents(int j, int i, int &J0, int &Jn, int &I0, int &In) {
-    J0 = j >> 1;
+__device__ __forceinline__ void parents(int j, int i, int &J0, int &Jn, int &I0, int &In, int pj_off = 0) {
+    J0 = (j >> 1) + pj_off;
     Jn = J0 + ((j & 1) ? 1 : -1);
     I0 = i >> 1;
     In = I0 + ((i & 1) ? 1 : -1);
@@ -213,6 +213,7 @@ k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ 
         double ff = fscale * f[idx];
         double res = ff - (s.diag * x[idx] - fine_offdiag(s, c, x));
         if (r) r[idx] = res;
+        if (j < F.jo0 || j >= F.jo1) continue;
         v[0] += res * res;
         v[1] += res;
         v[2] += ff * ff;
@@ -270,6 +271,7 @@ k_cg_update(FineView F, double *__restrict__ x, double *__restrict__ r,
         x[idx] += alpha * p[idx];
         double rv = r[idx] - alpha * q[idx];
         r[idx] = rv;
+        if (j < F.jo0 || j >= F.jo1) continue;
         v[0] += rv * rv;
         v[1] += rv;
     }
@@ -288,6 +290,7 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
         long idx;
         if (!fine_index(F, j, i, idx)) continue;
         if (!(F.nb[idx] & NB_SELF)) continue;
+        if (j < F.jo0 || j >= F.jo1) continue;
         v[0] += (r[idx] - mr) * z[idx];
         v[1] += z[idx];
     }
@@ -325,7 +328,7 @@ k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restric
         double qv = s.diag * pc - off;
         pnew[idx] = pc;
         q[idx] = qv;
-        v[0] += pc * qv;
+        if (j >= F.jo0 && j < F.jo1) v[0] += pc * qv;
     }
     grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) scal[S_RZ0 + (it & 1)] = rznew;
@@ -479,7 +482,7 @@ __global__ void k_build_nb(FineView F, const int8_t *__restrict__ sm, uint8_t *_
 // Dirichlet wall couplings: the aggregate centre of level l sits (2^l+1)/2 fine
 // spacings from the wall, so the coupling shrinks by (2^(l-1)+1)/(2^l+1) per
 // level (2/3, 3/5, 5/9, ... -> 1/2) instead of the 1/2 of interior faces.
-__global__ void k_coarsen0(FineView F, Level L1, int periodic, double wallfac) {
+__global__ void k_coarsen0(FineView F, Level L1, int periodic, double wallfac, int pj_off) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= L1.nx || J >= L1.ny) return;
@@ -488,8 +491,8 @@ __global__ void k_coarsen0(FineView F, Level L1, int periodic, double wallfac) {
     int fluid = 0;
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 2; b++) {
-            int j = 2 * J + a, i = 2 * I + b;
-            if (j >= F.ny || i >= F.nx) continue;
+            int j = 2 * (J - pj_off) + a, i = 2 * I + b;
+            if (j < 0 || j >= F.ny || i >= F.nx) continue;
             long idx;
             if (!fine_index(F, j, i, idx)) continue;
             uint8_t c = F.nb[idx];
@@ -510,7 +513,7 @@ __global__ void k_coarsen0(FineView F, Level L1, int periodic, double wallfac) {
 }
 
 // level l -> l+1 coefficients (l >= 1)
-__global__ void k_coarsen(Level Lf, Level Lc, int periodic, double wallfac) {
+__global__ void k_coarsen(Level Lf, Level Lc, int periodic, double wallfac, int pj_off) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= Lc.nx || J >= Lc.ny) return;
@@ -519,8 +522,8 @@ __global__ void k_coarsen(Level Lf, Level Lc, int periodic, double wallfac) {
     int fluid = 0;
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 2; b++) {
-            int j = 2 * J + a, i = 2 * I + b;
-            if (j >= Lf.ny || i >= Lf.nx) continue;
+            int j = 2 * (J - pj_off) + a, i = 2 * I + b;
+            if (j < 0 || j >= Lf.ny || i >= Lf.nx) continue;
             long idx = (long)(j + 1) * Lf.pitch + i + 1;
             if (!(Lf.code[idx] & NB_SELF)) continue;
             fluid = 1;
@@ -553,9 +556,9 @@ __global__ void k_build_dinv(Level L, int periodic) {
 }
 
 // which of the three non-own parents of each fine cell are unknowns on the coarse level
-__device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, int periodic) {
+__device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, int periodic, int pj_off) {
     int J0, Jn, I0, In;
-    parents(j, i, J0, Jn, I0, In);
+    parents(j, i, J0, Jn, I0, In, pj_off);
     bool jin = Jn >= 0 && Jn < Lc.ny, iin = true;
     if (periodic) { if (In < 0) In += Lc.nx; else if (In >= Lc.nx) In -= Lc.nx; }
     else iin = In >= 0 && In < Lc.nx;
@@ -566,7 +569,7 @@ __device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, in
     return c;
 }
 
-__global__ void k_parent_bits0(FineView F, uint8_t *__restrict__ nb, Level Lc, int periodic) {
+__global__ void k_parent_bits0(FineView F, uint8_t *__restrict__ nb, Level Lc, int periodic, int pj_off) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= F.nx || j >= F.ny) return;
@@ -574,17 +577,17 @@ __global__ void k_parent_bits0(FineView F, uint8_t *__restrict__ nb, Level Lc, i
     if (!fine_index(F, j, i, idx)) return;
     uint8_t c = nb[idx];
     if (!(c & NB_SELF)) return;
-    nb[idx] = c | parent_bits(j, i, Lc, periodic);
+    nb[idx] = (c & 31) | parent_bits(j, i, Lc, periodic, pj_off);
 }
 
-__global__ void k_parent_bits(Level Lf, Level Lc, int periodic) {
+__global__ void k_parent_bits(Level Lf, Level Lc, int periodic, int pj_off) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= Lf.nx || j >= Lf.ny) return;
     long idx = (long)(j + 1) * Lf.pitch + i + 1;
     uint8_t c = Lf.code[idx];
     if (!(c & NB_SELF)) return;
-    Lf.code[idx] = c | parent_bits(j, i, Lc, periodic);
+    Lf.code[idx] = (c & 31) | parent_bits(j, i, Lc, periodic, pj_off);
 }
 
 __global__ void k_solver_mask(const int8_t *__restrict__ m, int8_t *__restrict__ sm, int n2, int n1,
@@ -613,6 +616,7 @@ static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
     V.ny = L.ny; V.nx = L.nx; V.pitch = L.pitch; V.periodic = periodic;
     V.cx = L.cx; V.cy = L.cy; V.dinv = L.dinv; V.code = L.code;
     V.dirichlet = dirichlet;
+    V.pj_off = 0;
     return V;
 }
 
@@ -626,11 +630,64 @@ void mg_free(f2d_ctx *c, int which) {
         cudaFree(L.wall);
         cudaFree(L.code);
     }
+    for (Level &L : M.glev) {
+        for (CT *p : {L.x, L.x2, L.b, L.r, L.cx, L.cy, L.dinv}) cudaFree(p);
+        cudaFree(L.mass);
+        cudaFree(L.wall);
+        cudaFree(L.code);
+    }
     M = Multigrid();
 }
 
+static int alloc_level(f2d_ctx *c, Level &L, int ny, int nx) {
+    L.ny = ny; L.nx = nx;
+    L.pitch = (L.nx + 2 + 1) & ~1;
+    L.n = (size_t)(L.ny + 2) * L.pitch;
+    for (CT **p : {&L.x, &L.x2, &L.b, &L.r, &L.cx, &L.cy, &L.dinv}) {
+        F2D_CUDA(cudaMalloc(p, L.n * sizeof(CT)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, L.n * sizeof(CT), c->stream));
+    }
+    for (double **p : {&L.mass, &L.wall}) {
+        F2D_CUDA(cudaMalloc(p, L.n * sizeof(double)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, L.n * sizeof(double), c->stream));
+    }
+    F2D_CUDA(cudaMalloc(&L.code, L.n));
+    F2D_CUDA(cudaMemsetAsync(L.code, 0, L.n, c->stream));
+    return F2D_OK;
+}
+
+static void free_setup_arrays(std::vector<Level> &lev) {
+    for (size_t l = 1; l < lev.size(); l++) {
+        cudaFree(lev[l].mass); lev[l].mass = nullptr;
+        cudaFree(lev[l].wall); lev[l].wall = nullptr;
+    }
+}
+
+// where the tail (single-CTA) part of the hierarchy starts, checking that the
+// x, b, r arrays of all tail levels fit in shared memory
+static int choose_tail(std::vector<Level> &lev, int first_allowed, int &tail) {
+    const int n = (int)lev.size();
+    tail = n - 1;
+    for (int l = n - 1; l >= std::max(first_allowed, 1); l--)
+        if ((long)lev[l].ny * lev[l].nx <= 4096 && n - l <= 16) tail = l;
+    auto need = [&](int from) {
+        size_t b = 0;
+        for (int l = from; l < n; l++) b += (size_t)3 * (lev[l].ny + 2) * (lev[l].nx + 2) * sizeof(CT);
+        return b;
+    };
+    while (tail < n - 1 && need(tail) > 200 * 1024) tail++;
+    if (need(tail) > 200 * 1024) {
+        set_error("coarsest multigrid level too large (%d x %d)", lev.back().ny, lev.back().nx);
+        return F2D_ERR_UNSUPPORTED;
+    }
+    return F2D_OK;
+}
+
+static int mg_build_slab(f2d_ctx *c, int which);
+
 int mg_build(f2d_ctx *c, int which) {
     mg_free(c, which);
+    if (c->dist.on) return mg_build_slab(c, which);
     Multigrid &M = c->mg[which];
     M.which = which;
     const int n1 = c->n1, n2 = c->n2, nh = c->nh;
@@ -656,6 +713,7 @@ int mg_build(f2d_ctx *c, int which) {
                 imin = std::min(imin, i); imax = std::max(imax, i);
             }
     M.nunknown = cnt;
+    M.n_global = (double)cnt;
     FineView &F = M.fine;
     F.n2 = n2; F.n1 = n1; F.periodic = xper; F.dirichlet = vert;
     F.cx = c->dy / c->dx; F.cy = c->dx / c->dy;
@@ -677,6 +735,7 @@ int mg_build(f2d_ctx *c, int which) {
     };
     F.oj = origin(jmin);
     F.ny = jmax + 1 - F.oj;
+    F.jo0 = 0; F.jo1 = F.ny; F.pj_off = 0;
     if (xper) { F.oi = nh; F.nx = c->cfg.nx; }
     else { F.oi = origin(imin); F.nx = imax + 1 - F.oi; }
 
@@ -736,23 +795,23 @@ int mg_build(f2d_ctx *c, int which) {
         if (need(M.tail) > 200 * 1024) { set_error("coarsest multigrid level too large (%d x %d)", M.lev.back().ny, M.lev.back().nx); return F2D_ERR_UNSUPPORTED; }
     }
     // coefficients, level by level
-    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0);
+    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0, 0);
     LAUNCH_CHECK(c);
     k_build_dinv<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(M.lev[1], xper);
     LAUNCH_CHECK(c);
     for (size_t l = 1; l + 1 < M.lev.size(); l++) {
         Level &Lc = M.lev[l + 1];
         double pw = std::ldexp(1.0, (int)l);   // 2^l, producing level l+1
-        k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.lev[l], Lc, xper, (pw + 1.0) / (2.0 * pw + 1.0));
+        k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.lev[l], Lc, xper, (pw + 1.0) / (2.0 * pw + 1.0), 0);
         LAUNCH_CHECK(c);
         k_build_dinv<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(Lc, xper);
         LAUNCH_CHECK(c);
     }
     // prolongation weights
-    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], xper);
+    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], xper, 0);
     LAUNCH_CHECK(c);
     for (size_t l = 1; l + 1 < M.lev.size(); l++) {
-        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper);
+        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper, 0);
         LAUNCH_CHECK(c);
     }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
@@ -760,6 +819,186 @@ int mg_build(f2d_ctx *c, int which) {
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
         cudaFree(M.lev[l].wall); M.lev[l].wall = nullptr;
     }
+    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2, &M.z2}) {
+        F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
+    }
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    M.built = true;
+    return F2D_OK;
+}
+
+// ---------------------------------------------------------------------------
+// slab mode (f2d_dist_init): the hierarchy of a y-slab.  Levels 0..T-1 ("tile
+// levels") are local: owned rows plus G ghost rows per interface, refreshed by
+// dist_exchange; from level T on the grid is small, every rank keeps the whole
+// (global) tail hierarchy and solves it redundantly after an all-gather.
+// ---------------------------------------------------------------------------
+static int exchange_level(f2d_ctx *c, Level &L, bool with_dinv) {
+    void *ct[3] = {L.cx, L.cy, L.dinv};
+    F2D_TRY(dist_exchange(c, with_dinv ? 3 : 2, ct, (size_t)L.pitch * sizeof(CT), L.ny, 1));
+    if (L.mass) {
+        void *db[2] = {L.mass, L.wall};
+        F2D_TRY(dist_exchange(c, 2, db, (size_t)L.pitch * sizeof(double), L.ny, 1));
+    }
+    return dist_exchange1(c, L.code, (size_t)L.pitch, L.ny, 1);
+}
+
+static int mg_build_slab(f2d_ctx *c, int which) {
+    Multigrid &M = c->mg[which];
+    const Dist &D = c->dist;
+    M.which = which;
+    const int n1 = c->n1, n2 = c->n2, nh = c->nh, G = D.G;
+    const int xper = c->cfg.xperiodic;
+    const bool vert = which != F2D_SOLVER_CENTERS;
+    const int gny = c->cfg.reserved[3];          // global interior rows
+    if (c->cfg.solver_kind != 0) { set_error("slab mode supports the fused PCG solver only"); return F2D_ERR_UNSUPPORTED; }
+    if (gny <= 0) { set_error("global ny missing from the configuration"); return F2D_ERR_ARG; }
+    M.gs = D.south ? G : 0;
+    M.gn = D.north ? G : 0;
+
+    int8_t *sm;
+    F2D_CUDA(cudaMalloc(&sm, c->n));
+    k_solver_mask<<<dim3((n1 + 127) / 128, n2), 128, 0, c->stream>>>(c->m(vert ? "mskv" : "msk"), sm, n2, n1, nh, xper);
+    LAUNCH_CHECK(c);
+    std::vector<int8_t> h(c->n);
+    F2D_CUDA(cudaMemcpyAsync(h.data(), sm, c->n, cudaMemcpyDeviceToHost, c->stream));
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+
+    FineView &F = M.fine;
+    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.dirichlet = vert;
+    F.cx = c->dy / c->dx; F.cy = c->dx / c->dy;
+    F.shift = (which == F2D_SOLVER_HELMHOLTZ) ? c->area * c->cfg.f0 * c->cfg.f0 / (c->cfg.g * c->cfg.H) : 0.0;
+    F.oj = D.south ? 0 : nh;
+    F.ny = (D.north ? n2 : n2 - nh) - F.oj;
+    F.oi = nh; F.nx = c->cfg.nx;
+    F.jo0 = M.gs; F.jo1 = F.ny - M.gn;
+    F.pj_off = M.gs / 2;
+    const int owned0 = F.jo1 - F.jo0;
+    // unknowns outside the window (wall halos) are not supported in slab mode
+    int64_t cnt = 0;
+    for (int j = 0; j < n2; j++)
+        for (int i = 0; i < n1; i++)
+            if (h[(size_t)j * n1 + i]) {
+                int lj = j - F.oj, li = i - F.oi;
+                if (lj < 0 || lj >= F.ny || li < 0 || li >= F.nx) {
+                    cudaFree(sm);
+                    set_error("slab mode needs the fluid inside the interior rows/columns");
+                    return F2D_ERR_UNSUPPORTED;
+                }
+                if (lj >= F.jo0 && lj < F.jo1) cnt++;
+            }
+    M.nunknown = cnt;
+    {
+        double v = (double)cnt;
+        F2D_CUDA(cudaMemcpyAsync(c->d_scal + 24, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        F2D_TRY(dist_allreduce(c, c->d_scal + 24, 1, false));
+        F2D_CUDA(cudaMemcpyAsync(&v, c->d_scal + 24, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        F2D_CUDA(cudaStreamSynchronize(c->stream));
+        M.n_global = v;
+    }
+    F2D_CUDA(cudaMalloc(&M.nb, c->n));
+    F.nb = M.nb;
+    k_build_nb<<<grd(n1, n2), blk(), 0, c->stream>>>(F, sm, M.nb);
+    LAUNCH_CHECK(c);
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(sm);
+    if (M.n_global == 0) { M.built = true; return F2D_OK; }
+
+    // tile levels: T = first level whose GLOBAL grid fits the tail kernel
+    int T = 1;
+    {
+        long gy = gny, gx = F.nx;
+        int own = owned0;
+        for (T = 1;; T++) {
+            if ((gy & 1) || (own & 1) || (xper && (gx & 1))) {
+                set_error("slab mode: rows per rank (%d) and nx must be divisible by 2^%d", owned0, T);
+                return F2D_ERR_UNSUPPORTED;
+            }
+            gy /= 2; own /= 2; gx = xper ? gx / 2 : (gx + 1) / 2;
+            if (gy * gx <= 4096) break;
+            if (own < G) { set_error("slab mode: too few rows per rank (%d) for %d ranks", owned0, D.world); return F2D_ERR_UNSUPPORTED; }
+        }
+    }
+    M.lev.resize(T + 1);
+    M.lev[0].ny = F.ny; M.lev[0].nx = F.nx;
+    {
+        int own = owned0, nx = F.nx;
+        for (int l = 1; l <= T; l++) {
+            own /= 2; nx = xper ? nx / 2 : (nx + 1) / 2;
+            F2D_TRY(alloc_level(c, M.lev[l], M.gs + own + M.gn, nx));
+        }
+    }
+    M.tail = T;
+    const int pj = F.pj_off;
+    // local coefficients, level by level, ghosts from the neighbours
+    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0, pj);
+    LAUNCH_CHECK(c);
+    for (int l = 1; l <= T; l++) {
+        Level &L = M.lev[l];
+        F2D_TRY(exchange_level(c, L, false));
+        k_build_dinv<<<grd(L.nx, L.ny), blk(), 0, c->stream>>>(L, xper);
+        LAUNCH_CHECK(c);
+        F2D_TRY(exchange_level(c, L, true));
+        if (l < T) {
+            double pw = std::ldexp(1.0, l);
+            k_coarsen<<<grd(M.lev[l + 1].nx, M.lev[l + 1].ny), blk(), 0, c->stream>>>(L, M.lev[l + 1], xper, (pw + 1.0) / (2.0 * pw + 1.0), pj);
+            LAUNCH_CHECK(c);
+        }
+    }
+    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], xper, pj);
+    LAUNCH_CHECK(c);
+    for (int l = 1; l < T; l++) {
+        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper, pj);
+        LAUNCH_CHECK(c);
+    }
+    // global tail hierarchy: level T gathered from the owners, coarser ones derived
+    {
+        const Level &LT = M.lev[T];
+        const int ownT = LT.ny - M.gs - M.gn;
+        M.tail_y0 = D.rank * ownT;
+        std::vector<std::pair<int, int>> sizes;
+        sizes.push_back({ownT * D.world, LT.nx});
+        while (true) {
+            int ny = sizes.back().first, nx = sizes.back().second;
+            if ((long)ny * nx <= 16 || sizes.size() >= 16) break;
+            if (xper && (nx & 1)) break;
+            if (ny == 1 && nx == 1) break;
+            sizes.push_back({(ny + 1) / 2, xper ? nx / 2 : (nx + 1) / 2});
+        }
+        M.glev.resize(sizes.size());
+        for (size_t l = 0; l < sizes.size(); l++) F2D_TRY(alloc_level(c, M.glev[l], sizes[l].first, sizes[l].second));
+        Level &G0 = M.glev[0];
+        if (G0.pitch != LT.pitch) { set_error("internal: tail pitch mismatch"); return F2D_ERR_STATE; }
+        const size_t r0 = (size_t)(1 + M.gs) * LT.pitch, rows = (size_t)ownT * LT.pitch;
+        F2D_TRY(dist_allgather_rows(c, LT.cx + r0, G0.cx + G0.pitch, rows * sizeof(CT)));
+        F2D_TRY(dist_allgather_rows(c, LT.cy + r0, G0.cy + G0.pitch, rows * sizeof(CT)));
+        F2D_TRY(dist_allgather_rows(c, LT.mass + r0, G0.mass + G0.pitch, rows * sizeof(double)));
+        F2D_TRY(dist_allgather_rows(c, LT.wall + r0, G0.wall + G0.pitch, rows * sizeof(double)));
+        F2D_TRY(dist_allgather_rows(c, LT.code + r0, G0.code + G0.pitch, rows));
+        k_build_dinv<<<grd(G0.nx, G0.ny), blk(), 0, c->stream>>>(G0, xper);
+        LAUNCH_CHECK(c);
+        for (size_t l = 0; l + 1 < M.glev.size(); l++) {
+            Level &Lc = M.glev[l + 1];
+            double pw = std::ldexp(1.0, (int)l + T);
+            k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.glev[l], Lc, xper, (pw + 1.0) / (2.0 * pw + 1.0), 0);
+            LAUNCH_CHECK(c);
+            k_build_dinv<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(Lc, xper);
+            LAUNCH_CHECK(c);
+        }
+        for (size_t l = 0; l + 1 < M.glev.size(); l++) {
+            k_parent_bits<<<grd(M.glev[l].nx, M.glev[l].ny), blk(), 0, c->stream>>>(M.glev[l], M.glev[l + 1], xper, 0);
+            LAUNCH_CHECK(c);
+        }
+        int dummy;
+        std::vector<Level> chk(M.glev.size() + 1);
+        for (size_t l = 0; l < M.glev.size(); l++) { chk[l + 1].ny = M.glev[l].ny; chk[l + 1].nx = M.glev[l].nx; }
+        F2D_TRY(choose_tail(chk, 1, dummy));
+        if (dummy != 1) { set_error("slab mode: the gathered tail grid does not fit one CTA"); return F2D_ERR_UNSUPPORTED; }
+    }
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    free_setup_arrays(M.lev);
+    for (Level &L : M.glev) { cudaFree(L.mass); L.mass = nullptr; cudaFree(L.wall); L.wall = nullptr; }
     for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2, &M.z2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
@@ -919,9 +1158,9 @@ static int set_smem(K kernel, size_t bytes) {
     return F2D_OK;
 }
 
-static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet) {
+static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, int pj_off) {
     CoarseArrays<CT> A;
-    A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.dirichlet = dirichlet;
+    A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.dirichlet = dirichlet; A.pj_off = pj_off;
     A.cx = L.cx; A.cy = L.cy; A.dinv = L.dinv; A.code = L.code;
     return A;
 }
@@ -941,7 +1180,7 @@ static int launch_down0(f2d_ctx *c, Multigrid &M, const double *xin, double *xou
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
     const Level &C = M.lev[1];
-    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / (double)M.nunknown,
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / M.n_global,
                                                C.ny, C.nx, C.pitch, C.b);
     LAUNCH_CHECK(c);
     return F2D_OK;
@@ -959,7 +1198,7 @@ static int launch_up0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout,
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
     if (DOT && (size_t)g.x * g.y * 2 > c->part_capacity) { set_error("reduction scratch too small"); return F2D_ERR_STATE; }
     const Level &C = M.lev[1];
-    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / (double)M.nunknown,
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / M.n_global,
                                                C.ny, C.nx, C.pitch, F.periodic, level_result(M, 1), c->d_part, c->d_count,
                                                c->d_scal + S_RZNEW);
     LAUNCH_CHECK(c);
@@ -970,7 +1209,7 @@ template <int NU, int WJ>
 static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_down(NU, true), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
-    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet)};
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
     auto kern = k_mg_down<CT, CT, false, true, NU, WJ, CoarseLevel<CT>>;
     size_t smem = Window<CT, false, WJ>::bytes();
     static bool once = false;
@@ -986,7 +1225,7 @@ template <int NU, int WJ>
 static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
-    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet)};
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
     auto kern = k_mg_up<CT, CT, false, false, NU, WJ, CoarseLevel<CT>>;
     size_t smem = ((Window<CT, false, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
     static bool once = false;
@@ -1017,43 +1256,86 @@ static int coarse_up(f2d_ctx *c, Multigrid &M, int l) {
 
 static int launch_tail(f2d_ctx *c, Multigrid &M) {
     TailArgs A;
-    const int nlev = (int)M.lev.size();
-    A.nlev = nlev - M.tail;
+    const bool slab = c->dist.on;
+    // slab mode: the tail works on the gathered (global) copies of its levels
+    std::vector<Level> &TL = slab ? M.glev : M.lev;
+    const int first = slab ? 0 : M.tail;
+    const int nlev = (int)TL.size();
+    A.nlev = nlev - first;
     A.periodic = M.fine.periodic; A.dirichlet = M.fine.dirichlet;
     A.nu1 = c->cfg.nu1 > 0 ? c->cfg.nu1 : 2;
     A.nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
-    const Level &last = M.lev[nlev - 1];
+    const Level &last = TL[nlev - 1];
     A.nsw = last.ny * last.nx <= 64 ? 8 : 24;
     int off = 0;
-    for (int l = M.tail; l < nlev; l++) {
-        const Level &L = M.lev[l];
+    for (int l = first; l < nlev; l++) {
+        const Level &L = TL[l];
         int sp = L.nx + 2;
-        A.lev[l - M.tail] = TailLevel{L.ny, L.nx, L.pitch, sp, off, L.x, L.b, L.cx, L.cy, L.dinv, L.code};
+        A.lev[l - first] = TailLevel{L.ny, L.nx, L.pitch, sp, off, L.x, L.b, L.cx, L.cy, L.dinv, L.code};
         off += 3 * (L.ny + 2) * sp;
+    }
+    if (slab) {   // right-hand side: every rank's owned rows of level `tail`
+        const Level &LT = M.lev[M.tail];
+        const int ownT = LT.ny - M.gs - M.gn;
+        F2D_TRY(dist_allgather_rows(c, LT.b + (size_t)(1 + M.gs) * LT.pitch, M.glev[0].b + M.glev[0].pitch,
+                                    (size_t)ownT * LT.pitch * sizeof(CT)));
     }
     size_t smem = (size_t)off * sizeof(CT);
     static size_t configured = 0;
     if (smem > configured) { F2D_TRY(set_smem(k_mg_tail, smem)); configured = smem; }
     k_mg_tail<<<1, 1024, smem, c->stream>>>(A);
     LAUNCH_CHECK(c);
+    if (slab) {   // my rows (owned + ghosts) of the global correction
+        Level &LT = M.lev[M.tail];
+        const Level &G0 = M.glev[0];
+        F2D_CUDA(cudaMemcpyAsync(LT.x + LT.pitch, G0.x + (size_t)(1 + M.tail_y0 - M.gs) * G0.pitch,
+                                 (size_t)LT.ny * LT.pitch * sizeof(CT), cudaMemcpyDeviceToDevice, c->stream));
+    }
     return F2D_OK;
 }
 
 // One fused V-cycle on  L x = fscale*f - mean  (mean taken from scal[sumr_slot]/N
 // when sumr_slot >= 0).  zero_guess: x is only written.  with_dot: the up leg
 // leaves (sum f x, sum x) in S_RZNEW, S_SUMZ.
+static int exchange_fine(f2d_ctx *c, const Multigrid &M, double *a) {
+    return dist_exchange1(c, a, (size_t)M.fine.n1 * sizeof(double), M.fine.ny, M.fine.oj);
+}
+static int exchange_coarse(f2d_ctx *c, const Level &L, CT *a) {
+    return dist_exchange1(c, a, (size_t)L.pitch * sizeof(CT), L.ny, 1);
+}
+
 static int vcycle_fused(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale,
                         bool zero_guess, int sumr_slot, bool with_dot, double *xout) {
     // down leg: zero guess writes M.z; otherwise reads x and writes M.z (out of
     // place).  up leg: reads M.z, writes xout (M.z2 for CG, x itself otherwise).
+    // Slab mode: the ghost rows of everything a leg wrote are refreshed from the
+    // owners before the next leg reads them.
+    const bool slab = c->dist.on;
     const int nu1 = std::min(c->cfg.nu1 > 0 ? c->cfg.nu1 : 2, 3), nu2 = std::min(c->cfg.nu2 > 0 ? c->cfg.nu2 : 2, 3);
     if (zero_guess) { NU_SWITCH(nu1, (launch_down0<NU, true>(c, M, M.z, M.z, f, fscale, sumr_slot))); }
     else { NU_SWITCH(nu1, (launch_down0<NU, false>(c, M, x, M.z, f, fscale, sumr_slot))); }
-    for (int l = 1; l < M.tail; l++) { NU_SWITCH(nu1, (coarse_down<NU>(c, M, l))); }
+    if (slab) {
+        F2D_TRY(exchange_fine(c, M, M.z));
+        if (M.tail > 1) F2D_TRY(exchange_coarse(c, M.lev[1], M.lev[1].b));
+    }
+    for (int l = 1; l < M.tail; l++) {
+        NU_SWITCH(nu1, (coarse_down<NU>(c, M, l)));
+        if (slab) {
+            F2D_TRY(exchange_coarse(c, M.lev[l], M.lev[l].x));
+            if (l + 1 < M.tail) F2D_TRY(exchange_coarse(c, M.lev[l + 1], M.lev[l + 1].b));
+        }
+    }
     F2D_TRY(launch_tail(c, M));
-    for (int l = M.tail - 1; l >= 1; l--) { NU_SWITCH(nu2, (coarse_up<NU>(c, M, l))); }
+    for (int l = M.tail - 1; l >= 1; l--) {
+        NU_SWITCH(nu2, (coarse_up<NU>(c, M, l)));
+        if (slab) F2D_TRY(exchange_coarse(c, M.lev[l], M.lev[l].x2));
+    }
     if (with_dot) { NU_SWITCH(nu2, (launch_up0<NU, true>(c, M, M.z, xout, f, fscale, sumr_slot))); }
     else { NU_SWITCH(nu2, (launch_up0<NU, false>(c, M, M.z, xout, f, fscale, sumr_slot))); }
+    if (slab) {
+        F2D_TRY(exchange_fine(c, M, xout));
+        if (with_dot) F2D_TRY(dist_allreduce(c, c->d_scal + S_RZNEW, 2, false));
+    }
     return F2D_OK;
 }
 
@@ -1151,7 +1433,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     if (!M.built) { set_error("solver %d not built (call f2d_set_mask; Helmholtz needs a qg/rsw model)", which); return F2D_ERR_STATE; }
     if (iters_out) *iters_out = 0;
     if (relres_out) *relres_out = 0.0;
-    if (M.nunknown == 0) return op_fill(c, x);
+    if (M.n_global == 0) return op_fill(c, x);
     const FineView &F = M.fine;
     cudaStream_t st = c->stream;
     const double rtol = c->cfg.solver_rtol > 0 ? c->cfg.solver_rtol : 1e-12;
@@ -1160,7 +1442,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const dim3 nblk = cg_grid(c, F);
     const bool singular = !F.dirichlet && F.shift == 0.0;
     const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
-    const double N = (double)M.nunknown, inv_n = 1.0 / N;
+    const double N = M.n_global, inv_n = 1.0 / N;
     double *S = c->d_scal;
     int it = 0;
     double relres = 0.0;
@@ -1183,8 +1465,11 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         }
     } else {
         // preconditioned conjugate gradients, M^-1 = one V-cycle from a zero guess
+        if (c->dist.on) F2D_TRY(exchange_fine(c, M, x));     // the first guess may come from anywhere
         k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
         LAUNCH_CHECK(c);
+        F2D_TRY(dist_allreduce(c, S + S_RR, 3, false));
+        if (c->dist.on) F2D_TRY(exchange_fine(c, M, M.r));
         F2D_TRY(read_scalars(c, S_RR, 3));
         double ff = c->h_scal[S_FF];
         if (ff == 0.0) {   // b == 0: the solution is 0 (up to the Neumann null space)
@@ -1211,8 +1496,11 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             k_cg_dir_apply<<<nblk, 256, 0, st>>>(F, unfused ? M.z : M.z2, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
                                                  c->d_part, c->d_count);
             LAUNCH_CHECK(c);
+            F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
             k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pnew, M.q, S, S_RZ0 + (it & 1), c->d_part, c->d_count, S + S_RR);
             LAUNCH_CHECK(c);
+            F2D_TRY(dist_allreduce(c, S + S_RR, 2, false));
+            if (c->dist.on) F2D_TRY(exchange_fine(c, M, M.r));
             std::swap(pold, pnew);
             F2D_TRY(read_scalars(c, S_RR, 2));
             relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
@@ -1227,6 +1515,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     c->max_relres = std::max(c->max_relres, relres);
     if (iters_out) *iters_out = it;
     if (relres_out) *relres_out = relres;
+    if (c->dist.on) F2D_TRY(exchange_fine(c, M, x));
     F2D_TRY(op_fill(c, x));
     if (!conv || !std::isfinite(relres)) {
         set_error("elliptic solve %d: relative residual %.3e after %d iterations (rtol %.1e)", which,

@@ -43,7 +43,7 @@ __host__ __device__ constexpr int halo_up(int nu) { return 2 * nu; }
 
 template <typename T>
 struct CoarseArrays {       // level l >= 1, halo-padded (ny+2) x pitch
-    int ny, nx, pitch, periodic, dirichlet;
+    int ny, nx, pitch, periodic, dirichlet, pj_off;
     const T *cx, *cy, *dinv;
     const uint8_t *code;
 };
@@ -70,6 +70,8 @@ struct FineLevel {
     __device__ __forceinline__ int ny() const { return F.ny; }
     __device__ __forceinline__ int nx() const { return F.nx; }
     __device__ __forceinline__ int dirichlet() const { return F.dirichlet; }
+    __device__ __forceinline__ int pj_off() const { return F.pj_off; }
+    __device__ __forceinline__ bool owned(int j) const { return j >= F.jo0 && j < F.jo1; }
     __device__ __forceinline__ long row(int j) const {
         int aj = F.oj + j;
         if (j < 0 || j >= F.ny || aj < 0 || aj >= F.n2) return -1;
@@ -89,6 +91,8 @@ struct CoarseLevel {
     __device__ __forceinline__ int ny() const { return A.ny; }
     __device__ __forceinline__ int nx() const { return A.nx; }
     __device__ __forceinline__ int dirichlet() const { return A.dirichlet; }
+    __device__ __forceinline__ int pj_off() const { return A.pj_off; }
+    __device__ __forceinline__ bool owned(int j) const { return true; }
     __device__ __forceinline__ long row(int j) const {
         if (j < 0 || j >= A.ny) return -1;
         return (long)(j + 1) * A.pitch + 1;
@@ -323,8 +327,9 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
     __syncthreads();
     for (int t = threadIdx.x; t < (TJ / 2) * (TI / 2); t += TILE_THREADS) {
         int cj = t / (TI / 2), ci = t - cj * (TI / 2);
-        int J = tj0 / 2 + cj, I = ti0 / 2 + ci;
-        if (J >= nyc || I >= nxc) continue;
+        int J = tj0 / 2 + cj, I = ti0 / 2 + ci;            // aggregate of fine rows 2J, 2J+1
+        int Jc = J + L.pj_off();                           // its row in the coarse array
+        if (Jc >= nyc || I >= nxc) continue;
         int a0 = 2 * J - wj0, b0 = 2 * I - wi0;
         T acc = T(0);
 #pragma unroll
@@ -336,7 +341,7 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
                 acc += wy * wx * W.Fat(par0, a0 + da, b0 + db);
             }
         }
-        bc[(long)(J + 1) * pitchc + I + 1] = (TC)acc;
+        bc[(long)(Jc + 1) * pitchc + I + 1] = (TC)acc;
     }
 }
 
@@ -370,7 +375,7 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
     for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
         int a = t / CI, b = t - a * CI;
-        int J = cj0 + a, I = ci0 + b;
+        int J = cj0 + a + L.pj_off(), I = ci0 + b;
         TC v = TC(0);
         if (J >= 0 && J < nyc) {
             if (periodic_c) I = wrap_col(I, nxc);
@@ -423,7 +428,7 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
                 if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
                 T xv = W.X[p];
                 xout[rb + ch] = xv;
-                if (DOT) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
+                if (DOT && L.owned(j)) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
             }
         }
     }

@@ -537,7 +537,12 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         F2D_TRY(guess_before(c, c->stage_hint, c->f("p")));
         F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
         F2D_TRY(guess_after(c, c->stage_hint, c->f("p")));
-        return launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct);
+        F2D_TRY((launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct)));
+        if (c->dist.on) {   // the next tendency reads omega +-3 rows, u and ke +-1
+            void *a[4] = {ux, uy, c->f("omega"), c->f("ke")};
+            F2D_TRY(dist_exchange(c, 4, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
+        }
+        return F2D_OK;
     }
     case F2D_MODEL_RSW:
         return launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct);
@@ -585,6 +590,10 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     else if (nc == 2) F2D_TRY(STAGE(2));
     else F2D_TRY(STAGE(3));
 #undef STAGE
+    if (c->dist.on) {   // ghost rows of the updated velocity
+        void *a[2] = {c->tmp[0], c->tmp[1]};
+        F2D_TRY(dist_exchange(c, 2, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
+    }
     if (bouss) {
         // buoyancy: tendency from the old b (the momentum kernel above has read it), then update
         F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
@@ -597,6 +606,7 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
         else if (nc == 2) k_addto<2><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], 0);
         else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], co[2]);
         LAUNCH_CHECK(c);
+        if (c->dist.on) F2D_TRY(dist_exchange1(c, y, (size_t)c->n1 * sizeof(double), c->n2, 0));
     }
     return model_diag_impl(c, true);
 }
@@ -626,8 +636,10 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
 int max_abs_U(f2d_ctx *c, double *out) {
     int nb = c->nsm * 8;
     k_maxabs<<<nb, 256, 0, c->stream>>>((long)c->n, c->f("u.x"), c->f("u.y"), c->idx2, c->idy2,
-                                        c->d_part, c->d_count, c->d_scal + 8);
+                                        c->d_part, c->d_count, c->d_scal + 12);
+    F2D_CUDA(cudaMemcpyAsync(c->d_scal + 8, c->d_scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     LAUNCH_CHECK(c);
+    F2D_TRY(dist_allreduce(c, c->d_scal + 8, 2, true));
     F2D_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     *out = c->h_scal[0] + c->h_scal[1];

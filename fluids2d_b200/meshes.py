@@ -11,6 +11,7 @@ from collections import namedtuple
 
 import numpy as np
 
+from . import slabs
 from ._cabi import Engine
 from .elliptic import Poisson2D
 
@@ -20,7 +21,10 @@ Stencil = namedtuple("stencil", ("x", "y"))
 class Mesh:
     def __init__(self, param):
         self.param = param
-        self.shape = get_shape(param)
+        nranks = getattr(param, "nranks", 1) or 1
+        self.slab = slabs.Slab(param.ny, param.halowidth, getattr(param, "rank", 0) or 0, nranks)
+        # one GPU: the reference's (ny+2nh, nx+2nh); several: this rank's slab
+        self.shape = (self.slab.n2, param.nx + 2 * param.halowidth)
         self.nx, self.ny = param.nx, param.ny
         self.dx = param.Lx / self.nx
         self.dy = param.Ly / self.ny
@@ -28,7 +32,8 @@ class Mesh:
         self.xshift = 1
         self.yshift = self.shape[-1]
         kind = {"pcg": 0, "mg": 1}[getattr(param, "solver", "pcg")]
-        self.engine = Engine(param, device=getattr(param, "device", 0),
+        self.engine = Engine(param, device=getattr(param, "device", 0), slab=self.slab,
+                             comm=slabs.communicator() if nranks > 1 else None,
                              solver_rtol=getattr(param, "solver_rtol", 0.0),
                              solver_maxit=getattr(param, "solver_maxit", 0), solver_kind=kind,
                              nu1=getattr(param, "solver_nu", 0), nu2=getattr(param, "solver_nu", 0),
@@ -55,7 +60,13 @@ class Mesh:
         self.msk = self._allocate()
         xs = slice(None) if self.param.xperiodic else slice(nh, -nh)
         ys = slice(None) if self.param.yperiodic else slice(nh, -nh)
-        self.msk[ys, xs] = 1
+        if self.slab.nranks > 1:
+            # rows of the global default mask that fall in this rank's window
+            g = np.zeros((self.ny + 2 * nh, self.shape[1]), dtype="i1")
+            g[ys, xs] = 1
+            self.msk[:] = g[self.slab.window()]
+        else:
+            self.msk[ys, xs] = 1
 
     def finalize(self):
         """Re-derive masks, slip coefficient, stencil orders and solvers from
@@ -80,7 +91,7 @@ class Mesh:
         return (idx + (0.5 if which in ("c", "y") else 0.0)) * self.dx
 
     def y(self, which):
-        idx = np.arange(self.ny + 2 * self.param.halowidth) - self.param.halowidth
+        idx = np.arange(self.slab.n2) + self.slab.row0 - self.param.halowidth
         return (idx + (0.5 if which in ("c", "x") else 0.0)) * self.dy
 
     def xy(self, which="c"):

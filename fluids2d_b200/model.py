@@ -116,7 +116,8 @@ class Model:
         if p.model == "rsw":
             c = (p.g * p.H) ** 0.5
             maxU = c / self.mesh.dx + c / self.mesh.dy
-        elif on_device:
+        elif on_device or getattr(p, "nranks", 1) > 1:
+            # device reduction (all-reduced over the slabs when there are several)
             maxU = self.mesh.engine.max_abs_U() + 1e-99
         else:
             import numpy as np

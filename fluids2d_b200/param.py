@@ -53,6 +53,8 @@ class Param:
         self.nthreads = 1
         # NEW: device / elliptic-solver controls (the reference has a direct solve)
         self.device = 0
+        self.rank = 0                # y-slab decomposition: this process's slab ...
+        self.nranks = 1              # ... out of nranks (one GPU each); see slabs.py
         self.solver = "pcg"          # "pcg": multigrid-preconditioned CG; "mg": plain V-cycles
         self.solver_rtol = 1e-12     # ||b - A x|| <= rtol ||b||
         self.solver_maxit = 100

@@ -67,7 +67,8 @@ typedef struct {
     int32_t solver_maxit;   /* 0 -> 100                                      */
     int32_t solver_kind;    /* 0 MG-preconditioned CG, 1 plain V-cycles      */
     int32_t nu1, nu2;       /* red-black sweeps before / after; 0 -> 2       */
-    int32_t reserved[8];    /* [0]: 1 + order of the first-guess extrapolation across
+    int32_t reserved[8];    /* [1], [2], [3]: slab decomposition, see f2d_dist_init;
+                             * [0]: 1 + order of the first-guess extrapolation across
                              * time steps for the solves inside f2d_step (0 = default
                              * = quadratic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic) */
 } f2d_config;
@@ -158,6 +159,22 @@ int f2d_timer_stop(f2d_ctx *ctx, float *ms);
  * mg.down0, mg.up0, mg.down1, mg.up1, mg.tail, cg.dir_apply, cg.update.
  * Clobbers scratch arrays and diagnostics: call it last. */
 int f2d_bench_kernel(f2d_ctx *ctx, const char *name, int reps, float *ms, double *alg_bytes);
+/* ---- y-slab decomposition over several GPUs, one process and one context per
+ *      GPU (new: the reference is single-process).  The context is created
+ *      for the LOCAL slab: cfg.ny = rows of the local arrays - 2*nh, where the
+ *      local arrays hold the owned rows plus cfg.reserved[1] (south) and
+ *      cfg.reserved[2] (north) ghost rows -- 8 at an interface with a
+ *      neighbour, 0 at a physical wall (whose nh halo rows are part of the
+ *      arrays as usual); cfg.reserved[3] = global ny.  f2d_dist_init joins the
+ *      NCCL communicator (id from f2d_dist_unique_id on rank 0, passed around
+ *      by the host program) and must precede f2d_set_mask.  Afterwards
+ *      f2d_step / f2d_solve / f2d_max_abs_U exchange ghost rows and reduce
+ *      scalars themselves; state arrays are uploaded / downloaded per slab. */
+int f2d_dist_unique_id(char *id128);
+int f2d_dist_init(f2d_ctx *ctx, int rank, int world, const char *id128);
+/* refresh the ghost rows of one field from the owners (after an upload) */
+int f2d_dist_exchange(f2d_ctx *ctx, const char *field);
+int f2d_exchange_count(f2d_ctx *ctx, int64_t *count);
 /* number of kernels this context has launched so far */
 int f2d_launch_count(f2d_ctx *ctx, int64_t *count);
 
