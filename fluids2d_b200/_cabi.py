@@ -178,6 +178,7 @@ class Engine:
             if comm is None:
                 raise F2DError(-2, "a slab engine needs the NCCL identity (slabs.set_communicator)")
             rank, world, uid = comm
+            _preload_nccl()
             assert (rank, world) == (self.slab.rank, self.slab.nranks)
             self._chk(self.lib.f2d_dist_init(self._h, rank, world, uid))
 
@@ -400,8 +401,25 @@ class Engine:
         return n.value
 
 
+def _preload_nccl():
+    """make the newest NCCL in the environment (torch's bundled copy) the one
+    this process uses, before libf2d dlopens "libnccl.so.2" by soname"""
+    import importlib.util
+    import glob
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            for path in glob.glob(os.path.join(root, "lib", "libnccl.so*")):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return path
+    except Exception:
+        pass
+    return None
+
+
 def nccl_unique_id():
     """128-byte NCCL unique id (call on one rank, hand it to the others)"""
+    _preload_nccl()
     lib = load()
     buf = C.create_string_buffer(128)
     st = lib.f2d_dist_unique_id(buf)

@@ -41,7 +41,7 @@ def build_one(exact=False, force=False, verbose=False):
         cmd += ["-fmad=false", "-DF2D_EXACT"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
     return out
 

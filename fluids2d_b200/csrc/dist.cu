@@ -3,9 +3,58 @@
 // 8 x B200 box).  Rows are contiguous in every array of the path (row-major,
 // yshift = n1), so a ghost exchange is one contiguous message per direction and
 // array: no packing kernels.
+//
+// NCCL is bound at run time (dlopen), not at link time: a process that also
+// imports torch must end up with ONE libnccl.so.2, and torch's bundled copy is
+// newer than the system one.  Whoever loads first wins the soname, so the
+// library is only opened when a slab context is actually created (the Python
+// layer pre-loads torch's copy when it can find it).
+#include <dlfcn.h>
+
 #include "engine.cuh"
 
 namespace f2d {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.handle) return F2D_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error("cannot load libnccl.so.2: %s", dlerror()); return F2D_ERR_UNSUPPORTED; }
+#define SYM(field, name)                                                             \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));         \
+    if (!g_nccl.field) { set_error("libnccl lacks %s", name); return F2D_ERR_UNSUPPORTED; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return F2D_OK;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclGetErrorString g_nccl.GetErrorString
 
 #define F2D_NCCL(call)                                                            \
     do {                                                                          \
@@ -77,6 +126,7 @@ int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id) {
         return F2D_ERR_UNSUPPORTED;
     }
     if (c->cfg.yperiodic) { set_error("yperiodic is not supported with slabs"); return F2D_ERR_UNSUPPORTED; }
+    F2D_TRY(nccl_load());
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "unique id size");
     memcpy(&id, unique_id, sizeof(id));
@@ -89,6 +139,7 @@ int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id) {
 }
 
 int dist_unique_id(char *out) {
+    F2D_TRY(nccl_load());
     ncclUniqueId id;
     F2D_NCCL(ncclGetUniqueId(&id));
     memcpy(out, &id, sizeof(id));
