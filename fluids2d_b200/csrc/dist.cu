@@ -88,6 +88,34 @@ int dist_exchange(f2d_ctx *c, int narr, void *const *base, size_t row_bytes, lon
     return F2D_OK;
 }
 
+// several arrays of different geometry in one NCCL group; the arguments point
+// into an array of structs with the given stride (bytes)
+int dist_exchange_parts(f2d_ctx *c, int n, char *const *base, const size_t *row_bytes, const long *nrows,
+                        const long *row0, size_t stride) {
+    const Dist &D = c->dist;
+    if (!D.on || (!D.south && !D.north)) return F2D_OK;
+    auto at = [&](const void *p, int k) { return reinterpret_cast<const char *>(p) + (size_t)k * stride; };
+    F2D_NCCL(ncclGroupStart());
+    for (int k = 0; k < n; k++) {
+        char *b = *reinterpret_cast<char *const *>(at(base, k));
+        size_t rb = *reinterpret_cast<const size_t *>(at(row_bytes, k));
+        long nr = *reinterpret_cast<const long *>(at(nrows, k)), r0 = *reinterpret_cast<const long *>(at(row0, k));
+        char *p = b + (size_t)r0 * rb;
+        const size_t bytes = (size_t)D.G * rb;
+        if (D.north) {
+            F2D_NCCL(ncclSend(p + (size_t)(nr - 2 * D.G) * rb, bytes, ncclChar, D.rank + 1, D.comm, c->stream));
+            F2D_NCCL(ncclRecv(p + (size_t)(nr - D.G) * rb, bytes, ncclChar, D.rank + 1, D.comm, c->stream));
+        }
+        if (D.south) {
+            F2D_NCCL(ncclSend(p + (size_t)D.G * rb, bytes, ncclChar, D.rank - 1, D.comm, c->stream));
+            F2D_NCCL(ncclRecv(p, bytes, ncclChar, D.rank - 1, D.comm, c->stream));
+        }
+    }
+    F2D_NCCL(ncclGroupEnd());
+    c->exchanges++;
+    return F2D_OK;
+}
+
 int dist_exchange1(f2d_ctx *c, void *base, size_t row_bytes, long nrows, long row0) {
     void *b[1] = {base};
     return dist_exchange(c, 1, b, row_bytes, nrows, row0);

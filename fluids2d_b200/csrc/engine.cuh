@@ -103,7 +103,8 @@ struct Multigrid {
     int jo0 = 0, jo1 = 0;             // owned logical rows of the fine level [jo0, jo1)
     int tail_y0 = 0;                  // slab mode: first owned row of level `tail` in the global tail grid
     double n_global = 0;              // unknowns over all ranks
-    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr, *z2 = nullptr;   // CG vectors (n2,n1)
+    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr;   // CG vectors (n2,n1)
+    float *zf = nullptr, *zf2 = nullptr;   // preconditioned residual z = M r: fp32 (mg_tiles.cuh)
     int tail = 1;                     // first level handled by the single-CTA tail kernel
     int64_t nunknown = 0;
 };
@@ -176,6 +177,8 @@ int mg_apply(f2d_ctx *c, int which, const double *x, double *y);
 // dist.cu
 int dist_exchange(f2d_ctx *c, int narr, void *const *base, size_t row_bytes, long nrows, long row0);
 int dist_exchange1(f2d_ctx *c, void *base, size_t row_bytes, long nrows, long row0);
+int dist_exchange_parts(f2d_ctx *c, int n, char *const *base, const size_t *row_bytes, const long *nrows,
+                        const long *row0, size_t stride);
 int dist_allreduce(f2d_ctx *c, double *d_vals, int n, bool max_op);
 int dist_allgather_rows(f2d_ctx *c, const void *src_rows, void *dst, size_t bytes_per_rank);
 int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id);

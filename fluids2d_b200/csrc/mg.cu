@@ -303,8 +303,9 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
 //   pold / pnew are distinct buffers because q needs pnew at the neighbours.
 //   singular operators: z is projected on the complement of the constants, so
 //   that rounding in the V-cycle cannot feed the null space.
+template <typename TZ>
 __global__ void __launch_bounds__(256)
-k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restrict__ pold,
+k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ pold,
                double *__restrict__ pnew, double *__restrict__ q, double *__restrict__ scal, int it,
                int singular, double inv_n, double *part, unsigned int *count) {
     double rznew = scal[S_RZNEW];
@@ -318,7 +319,7 @@ k_cg_dir_apply(FineView F, const double *__restrict__ z, const double *__restric
         uint8_t c = F.nb[idx];
         if (!(c & NB_SELF)) continue;
         Stencil s = fine_stencil(F, i, idx, c);
-        auto P = [&](long k) { return (z[k] - mz) + beta * pold[k]; };
+        auto P = [&](long k) { return ((double)z[k] - mz) + beta * pold[k]; };
         double pc = P(idx);
         double off = 0.0;
         if (c & NB_W) off += s.cw * P(s.iw);
@@ -623,7 +624,9 @@ static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
 void mg_free(f2d_ctx *c, int which) {
     Multigrid &M = c->mg[which];
     cudaFree(M.nb);
-    for (double *p : {M.r, M.z, M.p, M.q, M.p2, M.z2}) cudaFree(p);
+    for (double *p : {M.r, M.z, M.p, M.q, M.p2}) cudaFree(p);
+    cudaFree(M.zf);
+    cudaFree(M.zf2);
     for (Level &L : M.lev) {
         for (CT *p : {L.x, L.x2, L.b, L.r, L.cx, L.cy, L.dinv}) cudaFree(p);
         cudaFree(L.mass);
@@ -819,9 +822,13 @@ int mg_build(f2d_ctx *c, int which) {
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
         cudaFree(M.lev[l].wall); M.lev[l].wall = nullptr;
     }
-    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2, &M.z2}) {
+    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
+    }
+    for (float **p : {&M.zf, &M.zf2}) {
+        F2D_CUDA(cudaMalloc(p, c->n * sizeof(float)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(float), c->stream));
     }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     M.built = true;
@@ -999,9 +1006,13 @@ static int mg_build_slab(f2d_ctx *c, int which) {
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     free_setup_arrays(M.lev);
     for (Level &L : M.glev) { cudaFree(L.mass); L.mass = nullptr; cudaFree(L.wall); L.wall = nullptr; }
-    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2, &M.z2}) {
+    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
+    }
+    for (float **p : {&M.zf, &M.zf2}) {
+        F2D_CUDA(cudaMalloc(p, c->n * sizeof(float)));
+        F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(float), c->stream));
     }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     M.built = true;
@@ -1050,13 +1061,14 @@ __device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const CT *x, int 
 
 __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
     TailSm S = tail_sm(sm, L);
-    TAIL_LOOP(L) {
-        if (((I + J) & 1) != color) continue;
-        CT di = __ldg(L.dinv + (long)(J + 1) * L.pitch + I + 1);
-        int s = (J + 1) * L.sp + I + 1;
-        CT a = zero ? CT(0) : tail_offdiag(L, S.x, periodic, J, I);
-        S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
-    }
+    // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
+    for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
+        for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) {
+            CT di = __ldg(L.dinv + (long)(J + 1) * L.pitch + I + 1);
+            int s = (J + 1) * L.sp + I + 1;
+            CT a = zero ? CT(0) : tail_offdiag(L, S.x, periodic, J, I);
+            S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
+        }
     __syncthreads();
 }
 
@@ -1105,8 +1117,8 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
 #pragma unroll
                 for (int b = -1; b <= 2; b++) {
                     int i = 2 * I + b;
-                    if (per) i = wrap_mod(i, L.nx);
-                    else if (i < 0 || i >= L.nx) continue;
+                    if (per) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
+                    if (i < 0 || i >= L.nx) continue;
                     CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
                     acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
                 }
@@ -1169,13 +1181,15 @@ static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, i
 // in place, the tile kernels write their up leg to the second buffer
 static const CT *level_result(const Multigrid &M, int l) { return l >= M.tail ? M.lev[l].x : M.lev[l].x2; }
 
-template <int NU, bool ZERO>
-static int launch_down0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout, const double *f, double fscale, int sumr_slot) {
+// fine-level legs.  FT = float: the CG preconditioner (z = M r) relaxes in fp32
+// on the fp64 residual and stores z in fp32; FT = double: plain V-cycles on x itself.
+template <typename FT, int NU, bool ZERO>
+static int launch_down0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const double *f, double fscale, int sumr_slot) {
     constexpr int WJ = 64, H = halo_down(NU, ZERO), TJ = WJ - 2 * H, TI = TW - 2 * H;
     const FineView &F = M.fine;
     FineLevel L{F};
-    auto kern = k_mg_down<double, CT, true, ZERO, NU, WJ, FineLevel>;
-    size_t smem = Window<double, true, WJ>::bytes();
+    auto kern = k_mg_down<FT, FT, double, CT, true, ZERO, NU, WJ, FineLevel>;
+    size_t smem = Window<FT, true, WJ>::bytes();
     static bool once = false;
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
@@ -1186,13 +1200,13 @@ static int launch_down0(f2d_ctx *c, Multigrid &M, const double *xin, double *xou
     return F2D_OK;
 }
 
-template <int NU, bool DOT>
-static int launch_up0(f2d_ctx *c, Multigrid &M, const double *xin, double *xout, const double *f, double fscale, int sumr_slot) {
+template <typename FT, int NU, bool DOT>
+static int launch_up0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const double *f, double fscale, int sumr_slot) {
     constexpr int WJ = 64, H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
     const FineView &F = M.fine;
     FineLevel L{F};
-    auto kern = k_mg_up<double, CT, true, DOT, NU, WJ, FineLevel>;
-    size_t smem = ((Window<double, true, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
+    auto kern = k_mg_up<FT, FT, double, CT, true, DOT, NU, WJ, FineLevel>;
+    size_t smem = ((Window<FT, true, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
     static bool once = false;
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
@@ -1210,7 +1224,7 @@ static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_down(NU, true), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
     CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
-    auto kern = k_mg_down<CT, CT, false, true, NU, WJ, CoarseLevel<CT>>;
+    auto kern = k_mg_down<CT, CT, CT, CT, false, true, NU, WJ, CoarseLevel<CT>>;
     size_t smem = Window<CT, false, WJ>::bytes();
     static bool once = false;
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
@@ -1226,7 +1240,7 @@ static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
     CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
-    auto kern = k_mg_up<CT, CT, false, false, NU, WJ, CoarseLevel<CT>>;
+    auto kern = k_mg_up<CT, CT, CT, CT, false, false, NU, WJ, CoarseLevel<CT>>;
     size_t smem = ((Window<CT, false, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
     static bool once = false;
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
@@ -1304,36 +1318,48 @@ static int exchange_coarse(f2d_ctx *c, const Level &L, CT *a) {
     return dist_exchange1(c, a, (size_t)L.pitch * sizeof(CT), L.ny, 1);
 }
 
-static int vcycle_fused(f2d_ctx *c, Multigrid &M, double *x, const double *f, double fscale,
-                        bool zero_guess, int sumr_slot, bool with_dot, double *xout) {
-    // down leg: zero guess writes M.z; otherwise reads x and writes M.z (out of
-    // place).  up leg: reads M.z, writes xout (M.z2 for CG, x itself otherwise).
+// ghost rows of what the down leg of level l wrote: x_l (M.z on the fine level)
+// and b_{l+1} (unless level l+1 is gathered for the tail)
+static int exchange_leg(f2d_ctx *c, Multigrid &M, int l, void *fine_x, size_t fine_elem) {
+    const Dist &D = c->dist;
+    if (!D.on || (!D.south && !D.north)) return F2D_OK;
+    struct Part { char *base; size_t row_bytes; long nrows, row0; } parts[2];
+    int np = 0;
+    if (l == 0) parts[np++] = Part{(char *)fine_x, (size_t)M.fine.n1 * fine_elem, M.fine.ny, M.fine.oj};
+    else parts[np++] = Part{(char *)M.lev[l].x, (size_t)M.lev[l].pitch * sizeof(CT), M.lev[l].ny, 1};
+    if (l + 1 < M.tail) parts[np++] = Part{(char *)M.lev[l + 1].b, (size_t)M.lev[l + 1].pitch * sizeof(CT), M.lev[l + 1].ny, 1};
+    return dist_exchange_parts(c, np, &parts[0].base, &parts[0].row_bytes, &parts[0].nrows, &parts[0].row0, sizeof(Part));
+}
+
+// FT = float: preconditioner z = M f (zero guess; M.zf -> xout = M.zf2, fp32);
+// FT = double: one V-cycle on x itself (x -> M.z -> x, fp64).
+template <typename FT>
+static int vcycle_fused(f2d_ctx *c, Multigrid &M, FT *work, const FT *xin, FT *xout, const double *f, double fscale,
+                        bool zero_guess, int sumr_slot, bool with_dot) {
+    // down leg: zero guess writes `work`; otherwise reads xin and writes `work`
+    // (out of place).  up leg: reads `work`, writes xout.
     // Slab mode: the ghost rows of everything a leg wrote are refreshed from the
     // owners before the next leg reads them.
     const bool slab = c->dist.on;
     const int nu1 = std::min(c->cfg.nu1 > 0 ? c->cfg.nu1 : 2, 3), nu2 = std::min(c->cfg.nu2 > 0 ? c->cfg.nu2 : 2, 3);
-    if (zero_guess) { NU_SWITCH(nu1, (launch_down0<NU, true>(c, M, M.z, M.z, f, fscale, sumr_slot))); }
-    else { NU_SWITCH(nu1, (launch_down0<NU, false>(c, M, x, M.z, f, fscale, sumr_slot))); }
-    if (slab) {
-        F2D_TRY(exchange_fine(c, M, M.z));
-        if (M.tail > 1) F2D_TRY(exchange_coarse(c, M.lev[1], M.lev[1].b));
-    }
+    if (zero_guess) { NU_SWITCH(nu1, (launch_down0<FT, NU, true>(c, M, work, work, f, fscale, sumr_slot))); }
+    else { NU_SWITCH(nu1, (launch_down0<FT, NU, false>(c, M, xin, work, f, fscale, sumr_slot))); }
+    // (each leg's outputs travel in ONE NCCL group: x of this level and the
+    // restricted right-hand side of the next)
+    if (slab) F2D_TRY(exchange_leg(c, M, 0, work, sizeof(FT)));
     for (int l = 1; l < M.tail; l++) {
         NU_SWITCH(nu1, (coarse_down<NU>(c, M, l)));
-        if (slab) {
-            F2D_TRY(exchange_coarse(c, M.lev[l], M.lev[l].x));
-            if (l + 1 < M.tail) F2D_TRY(exchange_coarse(c, M.lev[l + 1], M.lev[l + 1].b));
-        }
+        if (slab) F2D_TRY(exchange_leg(c, M, l, nullptr, 0));
     }
     F2D_TRY(launch_tail(c, M));
     for (int l = M.tail - 1; l >= 1; l--) {
         NU_SWITCH(nu2, (coarse_up<NU>(c, M, l)));
         if (slab) F2D_TRY(exchange_coarse(c, M.lev[l], M.lev[l].x2));
     }
-    if (with_dot) { NU_SWITCH(nu2, (launch_up0<NU, true>(c, M, M.z, xout, f, fscale, sumr_slot))); }
-    else { NU_SWITCH(nu2, (launch_up0<NU, false>(c, M, M.z, xout, f, fscale, sumr_slot))); }
+    if (with_dot) { NU_SWITCH(nu2, (launch_up0<FT, NU, true>(c, M, work, xout, f, fscale, sumr_slot))); }
+    else { NU_SWITCH(nu2, (launch_up0<FT, NU, false>(c, M, work, xout, f, fscale, sumr_slot))); }
     if (slab) {
-        F2D_TRY(exchange_fine(c, M, xout));
+        F2D_TRY(dist_exchange1(c, xout, (size_t)M.fine.n1 * sizeof(FT), M.fine.ny, M.fine.oj));
         if (with_dot) F2D_TRY(dist_allreduce(c, c->d_scal + S_RZNEW, 2, false));
     }
     return F2D_OK;
@@ -1461,7 +1487,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             if (!(relres > rtol)) { conv = true; break; }
             if (it == maxit) break;
             if (unfused) F2D_TRY(vcycle_unfused(c, M, x, b, fscale, false));
-            else F2D_TRY(vcycle_fused(c, M, x, b, fscale, false, -1, false, x));
+            else F2D_TRY(vcycle_fused<double>(c, M, M.z, x, x, b, fscale, false, -1, false));
         }
     } else {
         // preconditioned conjugate gradients, M^-1 = one V-cycle from a zero guess
@@ -1491,10 +1517,14 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
             } else {
-                F2D_TRY(vcycle_fused(c, M, nullptr, M.r, 1.0, true, slot, true, M.z2));
+                F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
             }
-            k_cg_dir_apply<<<nblk, 256, 0, st>>>(F, unfused ? M.z : M.z2, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
-                                                 c->d_part, c->d_count);
+            if (unfused)
+                k_cg_dir_apply<double><<<nblk, 256, 0, st>>>(F, M.z, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
+                                                             c->d_part, c->d_count);
+            else
+                k_cg_dir_apply<float><<<nblk, 256, 0, st>>>(F, M.zf2, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
+                                                            c->d_part, c->d_count);
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
             k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pnew, M.q, S, S_RZ0 + (it & 1), c->d_part, c->d_count, S + S_RR);
@@ -1551,13 +1581,13 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < n; r++) {
             if (k == "mg.down0") {
-                // fused down leg, level 0: R r bits, W z + b1 (fp32, 1/4 of the points)
-                F2D_TRY((launch_down0<2, true>(c, M, M.z, M.z, M.r, 1.0, -1)));
-                *bytes = npts * (8 + 1 + 8 + 1);
+                // fused down leg, level 0: R r (fp64) bits, W z (fp32) + b1 (fp32, 1/4 of the points)
+                F2D_TRY((launch_down0<float, 2, true>(c, M, M.zf, M.zf, M.r, 1.0, -1)));
+                *bytes = npts * (8 + 1 + 4 + 1);
             } else if (k == "mg.up0") {
-                // fused up leg, level 0: R z r bits x1 (fp32, 1/4), W z2
-                F2D_TRY((launch_up0<2, true>(c, M, M.z, M.z2, M.r, 1.0, -1)));
-                *bytes = npts * (8 + 8 + 1 + 1 + 8);
+                // fused up leg, level 0: R z (fp32) r (fp64) bits x1 (fp32, 1/4), W z2 (fp32)
+                F2D_TRY((launch_up0<float, 2, true>(c, M, M.zf, M.zf2, M.r, 1.0, -1)));
+                *bytes = npts * (4 + 8 + 1 + 1 + 4);
             } else if (k == "mg.down1") {
                 F2D_TRY((coarse_down<2>(c, M, 1)));
                 *bytes = (double)M.lev[1].ny * M.lev[1].nx * (4 * 4 + 1 + 4 + 1);
@@ -1573,8 +1603,8 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 *bytes = npts * (1.5 * 8 + 0.5);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.dir_apply") {
-                k_cg_dir_apply<<<nblk, 256, 0, c->stream>>>(F, M.z, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
-                *bytes = npts * (4 * 8 + 1);
+                k_cg_dir_apply<float><<<nblk, 256, 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
+                *bytes = npts * (4 + 3 * 8 + 1);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.update") {
                 k_cg_update<<<nblk, 256, 0, c->stream>>>(F, M.z, M.r, M.p, M.q, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP);

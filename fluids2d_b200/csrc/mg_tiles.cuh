@@ -212,14 +212,16 @@ struct Window {
     }
 
     // global -> shared: every load of a thread is issued before its first use
-    template <bool LOAD_X, class Lev>
-    __device__ __forceinline__ void load(const Lev &L, const T *__restrict__ xin, const T *__restrict__ fin,
-                                         T fscale, T fshift, int wj0, int wi0, int par0) {
+    template <bool LOAD_X, class Lev, typename TX, typename TF>
+    __device__ __forceinline__ void load(const Lev &L, const TX *__restrict__ xin, const TF *__restrict__ fin,
+                                         double fscale, double fshift, int wj0, int wi0, int par0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
         const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
         constexpr int R = WJ / TILE_WARPS;
         static_assert(WJ % TILE_WARPS == 0, "window rows must be a multiple of the warp count");
-        T fv[R][2], xv[R][2], cxv[R][2], cyv[R][2], div[R][2];
+        TF fv[R][2];
+        TX xv[R][2];
+        T cxv[R][2], cyv[R][2], div[R][2];
         uint8_t bits[R][2];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -229,7 +231,8 @@ struct Window {
                 int ch = h ? c1 : c0;
                 bool ok = rb >= 0 && ch >= 0;
                 long g = ok ? rb + ch : 0;
-                fv[r][h] = xv[r][h] = cxv[r][h] = cyv[r][h] = div[r][h] = T(0);
+                fv[r][h] = TF(0); xv[r][h] = TX(0);
+                cxv[r][h] = cyv[r][h] = div[r][h] = T(0);
                 bits[r][h] = 0;
                 if (ok) {
                     if constexpr (FINE) {
@@ -255,11 +258,12 @@ struct Window {
                 B[p] = bits[r][h];
                 if constexpr (FINE) {
                     // masked entries of the field arrays may hold anything: select, do not multiply
-                    Fv[p] = self ? fscale * fv[r][h] - fshift : T(0);
-                    X[p] = self ? xv[r][h] : T(0);
+                    // (the residual is scaled and shifted in fp64 before it is narrowed)
+                    Fv[p] = self ? (T)(fscale * (double)fv[r][h] - fshift) : T(0);
+                    X[p] = self ? (T)xv[r][h] : T(0);
                 } else {
-                    Fv[p] = fv[r][h];
-                    X[p] = xv[r][h];
+                    Fv[p] = (T)fv[r][h];
+                    X[p] = (T)xv[r][h];
                     CX[p] = cxv[r][h]; CY[p] = cyv[r][h]; DI[p] = div[r][h];
                 }
             }
@@ -274,9 +278,11 @@ struct Window {
 //          array; ZERO = first guess is zero (x is only written).
 //   TC   : element type of the next coarser level
 // ---------------------------------------------------------------------------
-template <typename T, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
+//   TX / TF: storage types of x and f in global memory (the fine level of the
+//          CG preconditioner relaxes in fp32 on an fp64 residual)
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
-k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
+k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
           const double *__restrict__ scal, int sumr_slot, double inv_n,
           int nyc, int nxc, int pitchc, TC *__restrict__ bc) {
     constexpr int H = halo_down(NU, ZERO);
@@ -288,13 +294,13 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-    T fshift = T(0);
+    double fshift = 0.0;
     if constexpr (FINE) {
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
         W.fill_tables(&L.F, L.dirichlet());
-        if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
+        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
     } else W.fill_tables(nullptr, L.dirichlet());
-    W.template load<!ZERO>(L, xin, fin, (T)fscale, fshift, wj0, wi0, par0);
+    W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
     __syncthreads();
     // ---- NU sweeps, red then black
 #pragma unroll
@@ -320,7 +326,7 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
                 if (b < H || b >= TW - H || ch < 0) continue;
                 if (!(W.B[p] & NB_SELF)) continue;
                 if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
-                xout[rb + ch] = W.X[p];
+                xout[rb + ch] = (TX)W.X[p];
             }
         }
     }
@@ -348,9 +354,9 @@ k_mg_down(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__res
 // ---------------------------------------------------------------------------
 // UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
 // ---------------------------------------------------------------------------
-template <typename T, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
-k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restrict__ fin, double fscale,
+k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
         const double *__restrict__ scal, int sumr_slot, double inv_n,
         int nyc, int nxc, int pitchc, int periodic_c, const TC *__restrict__ xc,
         double *part, unsigned int *count, double *out) {
@@ -365,11 +371,11 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-    T fshift = T(0);
+    double fshift = 0.0;
     if constexpr (FINE) {
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
         W.fill_tables(&L.F, L.dirichlet());
-        if (sumr_slot >= 0) fshift = (T)(scal[sumr_slot] * inv_n);
+        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
     } else W.fill_tables(nullptr, L.dirichlet());
     // ---- coarse window
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
@@ -383,7 +389,7 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
         }
         XC[t] = v;
     }
-    W.template load<true>(L, xin, fin, (T)fscale, fshift, wj0, wi0, par0);
+    W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
     __syncthreads();
     // ---- prolongation on the whole window
 #pragma unroll
@@ -427,8 +433,12 @@ k_mg_up(Lev L, const T *__restrict__ xin, T *__restrict__ xout, const T *__restr
                 if (!(W.B[p] & NB_SELF)) continue;
                 if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
                 T xv = W.X[p];
-                xout[rb + ch] = xv;
-                if (DOT && L.owned(j)) { acc[0] += (double)W.Fv[p] * (double)xv; acc[1] += (double)xv; }
+                xout[rb + ch] = (TX)xv;
+                if (DOT && L.owned(j)) {
+                    // the dot uses the fp64 residual, not its narrowed copy in shared memory
+                    double fv = fscale * (double)fin[rb + ch] - fshift;
+                    acc[0] += fv * (double)xv; acc[1] += (double)xv;
+                }
             }
         }
     }
