@@ -48,11 +48,12 @@ def turbulence_vorticity(x, y, area, seed=0, kpeak=8.0, kwidth=3.0, nmodes=96):
     return w * (area / np.sqrt(nmodes))
 
 
-def param_for(n, Param):
+def param_for(n, Param, ny_factor=1):
     p = Param()
     p.model = "euler"
-    p.nx = p.ny = n
-    p.Lx = p.Ly = 1.0
+    p.nx = n
+    p.ny = n * ny_factor
+    p.Lx, p.Ly = 1.0, 1.0 * ny_factor
     p.xperiodic = True
     p.integrator = "rk3"
     p.vortexforce = p.innerproduct = p.compflux = "weno"
@@ -140,7 +141,11 @@ def run_ours(args):
     import fluids2d_b200 as f2d
     f2d.Param._quiet = True
     n = args.n
-    p = param_for(n, f2d.Param)
+    # N > 1, default: WEAK scaling -- every GPU owns an n x n slab of one grid
+    # that is N times taller (n x nN cells, Ly = N); --strong keeps the n x n
+    # grid and splits it; --replicas runs N independent n x n grids.
+    weak = world > 1 and not args.strong and not args.replicas
+    p = param_for(n, f2d.Param, world if weak else 1)
     p.device = local
     if world > 1:
         torch.cuda.set_device(local)
@@ -207,7 +212,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     copies = world // world_slabs          # 1 when the grid is decomposed
-    value = copies * n * n * args.steps / (ms * 1e-3)
+    npoints = p.nx * p.ny                     # points of ONE grid
+    value = copies * npoints * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public per-step call, host buffers -----------
     integ.download(s)
@@ -227,7 +233,7 @@ def run_ours(args):
     if rank == 0:
         stop_evt.set()
         th.join()
-    e2e_value = copies * n * n * args.steps / e2e_s
+    e2e_value = copies * npoints * args.steps / e2e_s
     field_bytes = mesh.shape[0] * mesh.shape[1] * 8 * world    # all ranks together
     ok = bool(np.isfinite(s.u.x).all() and np.isfinite(s.omega).all())
 
@@ -259,11 +265,12 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if copies > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Euler {n}^2 fp64, x-periodic channel, WENO5-Z + SSP-RK3, "
-                                   "band-limited random vorticity (rng 0), fixed dt = CFL 0.9",
-                       "grid": [n, n], "dt": dt, "per_gpu": ("one independent replica per GPU" if copies > 1 else
-                                   (f"y-slab of {n // world} rows + 8 ghost rows per interface, NCCL halo exchange"
+            "scaling": "weak" if (copies > 1 or weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Euler {p.nx}x{p.ny} fp64, x-periodic channel, WENO5-Z + SSP-RK3, "
+                                   "band-limited random vorticity (rng 0), fixed dt = CFL 0.9"
+                                   + (f" ({n}^2 per GPU, weak scaling)" if weak else ""),
+                       "grid": [p.ny, p.nx], "dt": dt, "per_gpu": ("one independent replica per GPU" if copies > 1 else
+                                   (f"y-slab of {p.ny // world} rows + 8 ghost rows per interface, NCCL halo exchange"
                                     if world > 1 else "whole grid")),
                        "exchanges_per_step": nexch / max(args.steps, 1),
                        "l2_note": "every field is 134.6 MB > 126 MB L2; no flush needed",
@@ -313,6 +320,7 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=4096, help="grid size (default: the headline 4096)")
     ap.add_argument("--cpu-n", type=int, default=512, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N > 1: split the n x n grid instead of growing it with N")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent copies instead of one decomposed grid")
     ap.add_argument("--nu", type=int, default=2, help="smoothing sweeps per V-cycle leg")
     ap.add_argument("--guess", type=int, default=3, help="first-guess extrapolation order (0 off)")

@@ -103,6 +103,11 @@ struct Multigrid {
     int jo0 = 0, jo1 = 0;             // owned logical rows of the fine level [jo0, jo1)
     int tail_y0 = 0;                  // slab mode: first owned row of level `tail` in the global tail grid
     double n_global = 0;              // unknowns over all ranks
+    // CUDA graphs of one PCG iteration (first / odd / even), keyed by the solution array
+    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
+    const double *gx[3] = {nullptr, nullptr, nullptr};
+    int64_t glaunches[3] = {0, 0, 0}, gexchanges[3] = {0, 0, 0};
+    bool warm = false;
     double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr;   // CG vectors (n2,n1)
     float *zf = nullptr, *zf2 = nullptr;   // preconditioned residual z = M r: fp32 (mg_tiles.cuh)
     int tail = 1;                     // first level handled by the single-CTA tail kernel

@@ -623,6 +623,7 @@ static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
 
 void mg_free(f2d_ctx *c, int which) {
     Multigrid &M = c->mg[which];
+    for (cudaGraphExec_t &g : M.gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     cudaFree(M.nb);
     for (double *p : {M.r, M.z, M.p, M.q, M.p2}) cudaFree(p);
     cudaFree(M.zf);
@@ -1510,27 +1511,62 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         if (debug) fprintf(stderr, "[f2d] solve %d: initial relres %.3e\n", which, relres);
         double *pold = M.p, *pnew = M.p2;
         const int slot = singular ? S_SUMR : -1;   // lazy projection r - mean(r)
-        for (it = 0; !conv && it < maxit; it++) {
+        // One iteration = V-cycle + direction/apply + update (+ exchanges and
+        // all-reduces): a fixed sequence of ~16 launches.  It is captured once
+        // per parity class (first / odd / even iteration: the rz slot and the
+        // p ping-pong alternate) into a CUDA graph and replayed, which takes
+        // the launch and NCCL enqueue cost off the host.
+        auto iteration = [&](int iter, double *po, double *pn) -> int {
             if (unfused) {
                 if (singular) { k_cg_project<<<nblk, 256, 0, st>>>(F, M.r, S, inv_n); LAUNCH_CHECK(c); }
                 F2D_TRY(vcycle_unfused(c, M, M.z, M.r, 1.0, true));
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
+                k_cg_dir_apply<double><<<nblk, 256, 0, st>>>(F, M.z, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
+                                                             c->d_part, c->d_count);
             } else {
                 F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
-            }
-            if (unfused)
-                k_cg_dir_apply<double><<<nblk, 256, 0, st>>>(F, M.z, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
-                                                             c->d_part, c->d_count);
-            else
-                k_cg_dir_apply<float><<<nblk, 256, 0, st>>>(F, M.zf2, pold, pnew, M.q, S, it, singular ? 1 : 0, inv_n,
+                k_cg_dir_apply<float><<<nblk, 256, 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
                                                             c->d_part, c->d_count);
+            }
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
-            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pnew, M.q, S, S_RZ0 + (it & 1), c->d_part, c->d_count, S + S_RR);
+            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pn, M.q, S, S_RZ0 + (iter & 1), c->d_part, c->d_count, S + S_RR);
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_RR, 2, false));
             if (c->dist.on) F2D_TRY(exchange_fine(c, M, M.r));
+            return F2D_OK;
+        };
+        static const bool no_graph = getenv("F2D_NO_GRAPH") != nullptr;
+        const bool use_graph = !no_graph && !unfused && M.warm;
+        for (it = 0; !conv && it < maxit; it++) {
+            const int cls = it == 0 ? 0 : ((it & 1) ? 1 : 2);
+            if (use_graph) {
+                if (M.gexec[cls] && M.gx[cls] != x) {       // another x array: re-capture
+                    cudaGraphExecDestroy(M.gexec[cls]);
+                    M.gexec[cls] = nullptr;
+                }
+                if (!M.gexec[cls]) {
+                    cudaGraph_t graph = nullptr;
+                    const int64_t l0 = c->launches, e0 = c->exchanges;
+                    F2D_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    int rc = iteration(it, pold, pnew);
+                    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                    if (rc != F2D_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                    F2D_CUDA(ce);
+                    F2D_CUDA(cudaGraphInstantiate(&M.gexec[cls], graph, 0));
+                    cudaGraphDestroy(graph);
+                    M.gx[cls] = x;
+                    M.glaunches[cls] = c->launches - l0;
+                    M.gexchanges[cls] = c->exchanges - e0;
+                    c->launches = l0; c->exchanges = e0;    // counted when the graph runs
+                }
+                F2D_CUDA(cudaGraphLaunch(M.gexec[cls], st));
+                c->launches += M.glaunches[cls];
+                c->exchanges += M.gexchanges[cls];
+            } else {
+                F2D_TRY(iteration(it, pold, pnew));
+            }
             std::swap(pold, pnew);
             F2D_TRY(read_scalars(c, S_RR, 2));
             relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
@@ -1540,6 +1576,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             if (!(relres < 1e6 * best)) { it++; break; }   // diverging: give up, report
         }
     }
+    M.warm = true;      // every kernel attribute is set by now: later solves may capture graphs
     c->nsolves++;
     c->niters += it;
     c->max_relres = std::max(c->max_relres, relres);

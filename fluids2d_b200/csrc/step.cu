@@ -7,6 +7,7 @@
 // is the reference's flat-index arithmetic (weno.py:346-405), guarded by the
 // same stencil-order arrays, so interior results depend on the same operands.
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.cuh"
 #include "reduce.cuh"
@@ -286,6 +287,105 @@ k_diag(Grid g, const double *__restrict__ uxin, const double *__restrict__ uyin,
 }
 
 // ---------------------------------------------------------------------------
+// The same diagnostics for the projecting models, tiled through shared memory:
+// the projected velocity of a (64+6) x (16+6) window is formed ONCE per point
+// (1 velocity + 2 pressure loads) and the vorticity / kinetic-energy stencils
+// read it from shared memory, instead of re-projecting ~12 neighbours per
+// point from global memory.  Halo columns are computed in place like the
+// reference does and then overwritten by the periodic fill (k_fill_many).
+// ---------------------------------------------------------------------------
+constexpr int DTX = 64, DTY = 16, DH = 3, DWX = DTX + 2 * DH, DWY = DTY + 2 * DH;
+
+template <int MK>
+__global__ void __launch_bounds__(256)
+k_diag_tiled(Grid g, const double *__restrict__ uxin, const double *__restrict__ uyin,
+             const double *__restrict__ p, const int8_t *__restrict__ msk,
+             const int8_t *__restrict__ mskx, const int8_t *__restrict__ msky,
+             const int8_t *__restrict__ slip, const int8_t *__restrict__ okx,
+             const int8_t *__restrict__ oky, double *__restrict__ uxo, double *__restrict__ uyo,
+             double *__restrict__ Ux, double *__restrict__ Uy, double *__restrict__ omega,
+             double *__restrict__ ke) {
+    __shared__ double sux[DWY][DWX], suy[DWY][DWX];
+    const int i0 = blockIdx.x * DTX, j0 = blockIdx.y * DTY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const long s1 = g.n1;
+    for (int t = tid; t < DWY * DWX; t += 256) {
+        int a = t / DWX, b = t - a * DWX;
+        int j = j0 - DH + a, i = i0 - DH + b;
+        double vx = 0.0, vy = 0.0;
+        if (j >= 0 && j < g.n2 && i >= 0 && i < g.n1) {
+            long k = (long)j * s1 + i;
+            double pc = p[k];
+            vx = uxin[k];
+            vy = uyin[k];
+            if (i >= 1) vx -= (pc - p[k - 1]) * (double)mskx[k];      // addgrad, operators.py:49-53
+            if (j >= 1) vy -= (pc - p[k - s1]) * (double)msky[k];
+        }
+        sux[a][b] = vx;
+        suy[a][b] = vy;
+    }
+    __syncthreads();
+    const int b = DH + threadIdx.x, i = i0 + threadIdx.x;
+    if (i >= g.n1) return;
+#pragma unroll
+    for (int r = 0; r < DTY / 4; r++) {
+        const int a = DH + threadIdx.y + 4 * r, j = j0 + threadIdx.y + 4 * r;
+        if (j >= g.n2) break;
+        const long k = (long)j * s1 + i;
+        const double ux0 = sux[a][b], uy0 = suy[a][b];
+        uxo[k] = ux0;
+        uyo[k] = uy0;
+        Ux[k] = ux0 * g.idx2;
+        Uy[k] = uy0 * g.idy2;
+        double om = 0.0;
+        if (j >= 1) om = -(ux0 - sux[a - 1][b]);
+        if (i >= 1) om += uy0 - suy[a][b - 1];
+        omega[k] = om * (double)slip[k];
+        double e = 0.0;
+        if (MK == F2D_METHOD_CLASSIC) {
+            if (i <= g.n1 - 2) { double w = sux[a][b + 1]; e = w * (w * g.idx2) + ux0 * (ux0 * g.idx2); }
+            if (j <= g.n2 - 2) { double w = suy[a + 1][b]; e += w * (w * g.idy2) + uy0 * (uy0 * g.idy2); }
+            e *= (double)msk[k] * 0.25;
+        } else {
+            constexpr int M = MK > 3 ? 0 : MK;
+            int ox = okx[k];
+            if (ox > 0) {
+                double w3 = sux[a][b + 1];
+                double Um = 0.5 * (ux0 * g.idx2 + w3 * g.idx2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (ox > 2) { w1 = sux[a][b - 1]; w4 = sux[a][b + 2]; }
+                if (ox > 4) { w0 = sux[a][b - 2]; w5 = sux[a][b + 3]; }
+                e += recon<M>(ox, Um, w0, w1, ux0, w3, w4, w5) * Um;
+            }
+            int oy = oky[k];
+            if (oy > 0) {
+                double w3 = suy[a + 1][b];
+                double Um = 0.5 * (uy0 * g.idy2 + w3 * g.idy2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (oy > 2) { w1 = suy[a - 1][b]; w4 = suy[a + 2][b]; }
+                if (oy > 4) { w0 = suy[a - 2][b]; w5 = suy[a + 3][b]; }
+                e += recon<M>(oy, Um, w0, w1, uy0, w3, w4, w5) * Um;
+            }
+            e *= (double)msk[k] * 0.5;
+        }
+        ke[k] = e;
+    }
+}
+
+// meshes.py:135-143 for up to six arrays in one launch
+struct FillMany { double *a[6]; int n; };
+__global__ void k_fill_many(FillMany f, int n2, int n1, int nh) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n2 * 2 * nh) return;
+    int j = t / (2 * nh), kk = t % (2 * nh);
+    for (int q = 0; q < f.n; q++) {
+        double *row = f.a[q] + (size_t)j * n1;
+        if (kk < nh) row[kk] = row[n1 - 2 * nh + kk];
+        else row[n1 - nh + (kk - nh)] = row[nh + (kk - nh)];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // qg_projection of the tendency (operators.py:176-211), anomaly form
 // ---------------------------------------------------------------------------
 // pv = curl(du) * slip ; pv[1:,1:] += 1/4 sum4(dh * (-f0/H)) ; pv *= mskv
@@ -516,6 +616,35 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
     return F2D_OK;
 }
 
+static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin) {
+    static const bool untiled = getenv("F2D_UNTILED_DIAG") != nullptr;
+    if (untiled) return launch_diag<true, M_EULER>(c, uxin, uyin, c->cfg.innerproduct);
+    Grid g = grid_of(c);
+    dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
+#define TD_ARGS g, uxin, uyin, c->f("p"), c->m("msk"), c->m("mskx"), c->m("msky"), c->m("slip"), c->m("ok.x"), \
+                c->m("ok.y"), c->f("u.x"), c->f("u.y"), c->f("U.x"), c->f("U.y"), c->f("omega"), c->f("ke")
+    switch (c->cfg.innerproduct) {
+    case F2D_METHOD_WENO: k_diag_tiled<0><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
+    case F2D_METHOD_UPWIND: k_diag_tiled<1><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
+    case F2D_METHOD_CENTERED: k_diag_tiled<2><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
+    case F2D_METHOD_CWENO: k_diag_tiled<3><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
+    case F2D_METHOD_CLASSIC: k_diag_tiled<4><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
+    default: set_error("bad innerproduct method"); return F2D_ERR_ARG;
+    }
+#undef TD_ARGS
+    LAUNCH_CHECK(c);
+    if (c->cfg.xperiodic) {
+        FillMany f;
+        f.n = 6;
+        const char *names[6] = {"u.x", "u.y", "U.x", "U.y", "omega", "ke"};
+        for (int q = 0; q < 6; q++) f.a[q] = c->f(names[q]);
+        int tot = c->n2 * 2 * c->nh;
+        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+
 // `pre`: the un-projected velocity already sits in tmp[0..1] (fused stage kernel)
 static int model_diag_impl(f2d_ctx *c, bool pre) {
     if (!c->mesh_ready) { set_error("f2d_diag before f2d_set_mask"); return F2D_ERR_STATE; }
@@ -537,7 +666,7 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         F2D_TRY(guess_before(c, c->stage_hint, c->f("p")));
         F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
         F2D_TRY(guess_after(c, c->stage_hint, c->f("p")));
-        F2D_TRY((launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct)));
+        F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
         if (c->dist.on) {   // the next tendency reads omega +-3 rows, u and ke +-1
             void *a[4] = {ux, uy, c->f("omega"), c->f("ke")};
             F2D_TRY(dist_exchange(c, 4, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
@@ -693,7 +822,7 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 *bytes = npts * (3 * 8 + 1);
             } else if (k == "project_diag") {
                 // R p u.x u.y, W u.x u.y U.x U.y omega ke, masks msk mskx msky slip ok.x ok.y
-                F2D_TRY((launch_diag<true, M_EULER>(c, c->tmp[0], c->tmp[1], c->cfg.innerproduct)));
+                F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
                 *bytes = npts * (9 * 8 + 6);
             } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
         }
