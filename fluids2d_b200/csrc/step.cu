@@ -7,6 +7,7 @@
 // is the reference's flat-index arithmetic (weno.py:346-405), guarded by the
 // same stencil-order arrays, so interior results depend on the same operands.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "engine.cuh"
@@ -46,8 +47,15 @@ __device__ __forceinline__ int image_col(const Grid &g, int i) {
     const long s1 = (g).n1;                                  \
     (void)k_out; (void)s1;
 
-static dim3 blk2d() { return dim3(64, 4); }
-static dim3 grd2d(const f2d_ctx *c) { return dim3((c->n1 + 63) / 64, (c->n2 + 3) / 4); }
+static dim3 blk2d() {
+    static int bx = 0, by = 0;
+    if (!bx) {
+        bx = 64; by = 4;
+        if (const char *e = getenv("F2D_BLK")) { int x, y; if (sscanf(e, "%dx%d", &x, &y) == 2 && x * y <= 256) { bx = x; by = y; } }
+    }
+    return dim3(bx, by);
+}
+static dim3 grd2d(const f2d_ctx *c) { dim3 b = blk2d(); return dim3((c->n1 + b.x - 1) / b.x, (c->n2 + b.y - 1) / b.y); }
 
 enum { M_EULER = 0, M_BOUSS = 1, M_RSW = 2, M_QGRSW = 3 };
 
@@ -369,6 +377,91 @@ k_diag_tiled(Grid g, const double *__restrict__ uxin, const double *__restrict__
             e *= (double)msk[k] * 0.5;
         }
         ke[k] = e;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The fused tendency + Runge-Kutta update of the projecting models, tiled the
+// same way: omega, u.x, u.y, ke of a (64+6) x (16+6) window are staged in shared
+// memory once; the two variable-order reconstructions, the 4-point velocity
+// averages and the kinetic-energy gradient read them from there.  Same
+// arithmetic as k_rhs_mom, so the two agree bit for bit away from the periodic
+// halo columns (which k_fill_many overwrites, as mesh.fill does).
+// ---------------------------------------------------------------------------
+template <int MV, int MODEL, int NC>
+__global__ void __launch_bounds__(256)
+k_stage_tiled(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
+              const double *__restrict__ omega, const double *__restrict__ ke,
+              const double *__restrict__ bb, const int8_t *__restrict__ ovx,
+              const int8_t *__restrict__ ovy, const int8_t *__restrict__ mskx,
+              const int8_t *__restrict__ msky, double halfdy, double *__restrict__ dux,
+              double *__restrict__ duy, RkFuse rk) {
+    // omega needs the full 3-point halo; u.x, u.y, ke only one point
+    constexpr int H1 = 1, W1X = DTX + 2 * H1, W1Y = DTY + 2 * H1;
+    __shared__ double som[DWY][DWX], sux[W1Y][W1X], suy[W1Y][W1X], ske[W1Y][W1X];
+    const int i0 = blockIdx.x * DTX, j0 = blockIdx.y * DTY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const long s1 = g.n1;
+    for (int t = tid; t < DWY * DWX; t += 256) {
+        int a = t / DWX, b = t - a * DWX;
+        int j = j0 - DH + a, i = i0 - DH + b;
+        som[a][b] = (j >= 0 && j < g.n2 && i >= 0 && i < g.n1) ? omega[(long)j * s1 + i] : 0.0;
+    }
+    for (int t = tid; t < W1Y * W1X; t += 256) {
+        int a = t / W1X, b = t - a * W1X;
+        int j = j0 - H1 + a, i = i0 - H1 + b;
+        double vx = 0.0, vy = 0.0, vk = 0.0;
+        if (j >= 0 && j < g.n2 && i >= 0 && i < g.n1) {
+            long k = (long)j * s1 + i;
+            vx = ux[k]; vy = uy[k]; vk = ke[k];
+        }
+        sux[a][b] = vx; suy[a][b] = vy; ske[a][b] = vk;
+    }
+    __syncthreads();
+    const int b = DH + threadIdx.x, b1 = H1 + threadIdx.x, i = i0 + threadIdx.x;
+    if (i >= g.n1) return;
+#pragma unroll
+    for (int r = 0; r < DTY / 4; r++) {
+        const int a = DH + threadIdx.y + 4 * r, a1 = H1 + threadIdx.y + 4 * r, j = j0 + threadIdx.y + 4 * r;
+        if (j >= g.n2) break;
+        const long k = (long)j * s1 + i;
+        double rx = 0, ry = 0;
+        int oy = ovy[k];
+        if (oy > 0) {   // du.x: V = U.y, s = yshift, s2 = xshift, sign +1
+            double Vm = 0.25 * (((suy[a1][b1] * g.idy2 + suy[a1 + 1][b1] * g.idy2) + suy[a1][b1 - 1] * g.idy2) +
+                                suy[a1 + 1][b1 - 1] * g.idy2);
+            double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = som[a][b], w3 = som[a + 1][b];
+            if (oy > 2) { w1 = som[a - 1][b]; w4 = som[a + 2][b]; }
+            if (oy > 4) { w0 = som[a - 2][b]; w5 = som[a + 3][b]; }
+            rx = recon<MV>(oy, Vm, w0, w1, w2, w3, w4, w5) * Vm;
+        }
+        int ox = ovx[k];
+        if (ox > 0) {   // du.y: V = U.x, s = xshift, s2 = yshift, sign -1
+            double Vm = 0.25 * (((sux[a1][b1] * g.idx2 + sux[a1][b1 + 1] * g.idx2) + sux[a1 - 1][b1] * g.idx2) +
+                                sux[a1 - 1][b1 + 1] * g.idx2);
+            double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = som[a][b], w3 = som[a][b + 1];
+            if (ox > 2) { w1 = som[a][b - 1]; w4 = som[a][b + 2]; }
+            if (ox > 4) { w0 = som[a][b - 2]; w5 = som[a][b + 3]; }
+            ry = (-recon<MV>(ox, Vm, w0, w1, w2, w3, w4, w5)) * Vm;
+        }
+        if (i >= 1) rx -= (ske[a1][b1] - ske[a1][b1 - 1]) * (double)mskx[k];
+        if (j >= 1) ry -= (ske[a1][b1] - ske[a1 - 1][b1]) * (double)msky[k];
+        if (MODEL == M_BOUSS) {
+            if (j >= 1) ry += (halfdy * (bb[k] + bb[k - s1])) * (double)msky[k];
+        }
+        if (rk.write_ds) { dux[k] = rx; duy[k] = ry; }
+        double ax, ay;
+        if (NC == 1) { ax = rk.c[0] * rx; ay = rk.c[0] * ry; }
+        else {
+            ax = rk.c[0] * rk.dx[0][k]; ay = rk.c[0] * rk.dy[0][k];
+            if (NC == 2) { ax = ax + rk.c[1] * rx; ay = ay + rk.c[1] * ry; }
+            else {
+                ax = ax + rk.c[1] * rk.dx[1][k]; ay = ay + rk.c[1] * rk.dy[1][k];
+                ax = ax + rk.c[2] * rx; ay = ay + rk.c[2] * ry;
+            }
+        }
+        rk.ubx[k] = sux[a1][b1] + ax;
+        rk.uby[k] = suy[a1][b1] + ay;
     }
 }
 
@@ -700,6 +793,38 @@ static int rk_coefs(int integ, double dt, int stage, double *co) {
     return 0;
 }
 
+template <int MODEL, int NC>
+static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse &rk) {
+    // measured on B200 (4096^2): the L1-cached one-thread-per-point kernel
+    // (0.396 ms) beats this shared-memory version (0.456 ms); kept for study
+    static const bool tiled = getenv("F2D_TILED_STAGE") != nullptr;
+    if (!tiled) return launch_rhs_mom<MODEL, NC>(c, dux, duy, rk);
+    Grid g = grid_of(c);
+    const double *b = c->has("b") ? c->f("b") : nullptr;
+    dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
+#define ST_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"), b, c->m("ov.x"), c->m("ov.y"), \
+                c->m("mskx"), c->m("msky"), 0.5 * c->dy, dux, duy, rk
+    switch (c->cfg.vortexforce) {
+    case F2D_METHOD_WENO: k_stage_tiled<WENO, MODEL, NC><<<grd, blk, 0, c->stream>>>(ST_ARGS); break;
+    case F2D_METHOD_UPWIND: k_stage_tiled<UPWIND, MODEL, NC><<<grd, blk, 0, c->stream>>>(ST_ARGS); break;
+    case F2D_METHOD_CENTERED: k_stage_tiled<CENTERED, MODEL, NC><<<grd, blk, 0, c->stream>>>(ST_ARGS); break;
+    case F2D_METHOD_CWENO: k_stage_tiled<CWENO, MODEL, NC><<<grd, blk, 0, c->stream>>>(ST_ARGS); break;
+    default: set_error("bad vortexforce method"); return F2D_ERR_ARG;
+    }
+#undef ST_ARGS
+    LAUNCH_CHECK(c);
+    if (c->cfg.xperiodic) {
+        FillMany f;
+        f.n = 0;
+        if (rk.write_ds) { f.a[f.n++] = dux; f.a[f.n++] = duy; }
+        f.a[f.n++] = rk.ubx; f.a[f.n++] = rk.uby;
+        int tot = c->n2 * 2 * c->nh;
+        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+
 // Euler / Boussinesq stage with the velocity update fused into the tendency
 // kernel: u* = u + sum c_i ds_i lands in tmp[0..1], the projection writes u.
 static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
@@ -714,7 +839,7 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     double *dux = c->f(dsname(s, "u.x")), *duy = c->f(dsname(s, "u.y"));
     const bool bouss = c->cfg.model == F2D_MODEL_BOUSSINESQ;
 #define STAGE(NCV)                                                                     \
-    (bouss ? launch_rhs_mom<M_BOUSS, NCV>(c, dux, duy, rk) : launch_rhs_mom<M_EULER, NCV>(c, dux, duy, rk))
+    (bouss ? launch_stage_tiled<M_BOUSS, NCV>(c, dux, duy, rk) : launch_stage_tiled<M_EULER, NCV>(c, dux, duy, rk))
     if (nc == 1) F2D_TRY(STAGE(1));
     else if (nc == 2) F2D_TRY(STAGE(2));
     else F2D_TRY(STAGE(3));
@@ -806,7 +931,7 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 rk.c[0] = rk.c[1] = rk.c[2] = 0.0;
                 rk.dx[0] = c->f("ds0.u.x"); rk.dy[0] = c->f("ds0.u.y"); rk.dx[1] = rk.dy[1] = nullptr;
                 rk.ubx = c->tmp[0]; rk.uby = c->tmp[1]; rk.write_ds = 1;
-                F2D_TRY((launch_rhs_mom<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
+                F2D_TRY((launch_stage_tiled<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
                 *bytes = npts * (10 * 8 + 4);
             } else if (k == "rk_update") {
                 // R u ds0 ds1 ds2, W u (one component; coefficients 0 keep u intact)
