@@ -12,7 +12,8 @@ import numpy as np
 
 from . import build as _build
 
-MODELS = {"euler": 0, "boussinesq": 1, "rsw": 2, "qgrsw": 3}
+MODELS = {"euler": 0, "boussinesq": 1, "rsw": 2, "qgrsw": 3, "eulerpsi": 4, "qg": 5, "advection": 6,
+          "vectoradv": 7}
 METHODS = {"weno": 0, "upwind": 1, "centered": 2, "cweno": 3, "classic": 4}
 INTEGRATORS = {"rk3": 0, "ef": 1, "enrk3": 2}
 SOLVERS = {"c": 0, "v": 1, "h": 2}
@@ -128,7 +129,7 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
     """param.py:13-59 attributes -> f2d_config."""
     if param.model not in MODELS:
         raise NotImplementedError(
-            f"model '{param.model}' is outside the accelerated hot path (euler, boussinesq, rsw, qgrsw)")
+            f"model '{param.model}' is not on the device path ({', '.join(MODELS)})")
     if param.integrator not in INTEGRATORS:
         raise NotImplementedError(f"integrator '{param.integrator}' is not on the device path")
     if getattr(param, "tracer", None) not in (None, "None"):
@@ -149,6 +150,7 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
         if slab.rank < slab.nranks - 1:
             cfg.noslip &= ~NOSLIP["top"]
     cfg.f0, cfg.g, cfg.H = param.f0, param.g, param.H
+    cfg.reserved[4] = int(getattr(param, "beta", 0.0) != 0)
     cfg.integrator = INTEGRATORS[param.integrator]
     cfg.compflux = METHODS[param.compflux]
     cfg.vortexforce = METHODS[param.vortexforce]

@@ -49,7 +49,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     NEED(cfg->nx > 0 && cfg->ny > 0, "nx, ny must be positive");
     NEED(cfg->nh == 3, "halowidth must be 3 (the widest stencil reaches 3 cells, weno.py:353-355)");
     NEED(cfg->nx >= 2 * cfg->nh && cfg->ny >= 2 * cfg->nh, "nx, ny must be >= 2*halowidth");
-    NEED(cfg->model >= 0 && cfg->model <= F2D_MODEL_QGRSW, "unknown model %d", cfg->model);
+    NEED(cfg->model >= 0 && cfg->model <= F2D_MODEL_VECTORADV, "unknown model %d", cfg->model);
     NEED(cfg->integrator >= 0 && cfg->integrator <= F2D_INT_ENRK3, "unknown integrator %d", cfg->integrator);
     NEED(cfg->maxorder == 2 || cfg->maxorder == 4 || cfg->maxorder == 6, "maxorder must be 2, 4 or 6");
     NEED(cfg->vortexforce >= 0 && cfg->vortexforce <= 3, "unknown vortexforce method");
@@ -100,6 +100,22 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     case F2D_MODEL_QGRSW:
         names = {"u.x", "u.y", "h", "U.x", "U.y", "omega", "ke", "p", "flx.x", "flx.y", "pv", "psi"};
         c->prognostic = {"u.x", "u.y", "h"};
+        break;
+    case F2D_MODEL_EULERPSI:
+        names = {"omega", "U.x", "U.y", "psi", "vomega", "flx.x", "flx.y"};
+        c->prognostic = {"omega"};
+        break;
+    case F2D_MODEL_QG:
+        names = {"pv", "U.x", "U.y", "h", "flx.x", "flx.y", "work", "psi"};
+        c->prognostic = {"pv"};
+        break;
+    case F2D_MODEL_ADVECTION:
+        names = {"q", "U.x", "U.y", "flx.x", "flx.y"};
+        c->prognostic = {"q"};
+        break;
+    case F2D_MODEL_VECTORADV:
+        names = {"v.x", "v.y", "U.x", "U.y", "omega", "q"};
+        c->prognostic = {"v.x", "v.y"};
         break;
     }
     c->nstages = cfg->integrator == F2D_INT_EF ? 1 : 3;
@@ -164,7 +180,7 @@ int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
     // meshes.py:39-47
     F2D_TRY(mg_build(c, F2D_SOLVER_CENTERS));
     F2D_TRY(mg_build(c, F2D_SOLVER_VERTICES));
-    if (c->cfg.model == F2D_MODEL_RSW || c->cfg.model == F2D_MODEL_QGRSW)
+    if (c->cfg.model == F2D_MODEL_RSW || c->cfg.model == F2D_MODEL_QGRSW || c->cfg.model == F2D_MODEL_QG)
         F2D_TRY(mg_build(c, F2D_SOLVER_HELMHOLTZ));
     return F2D_OK;
 }

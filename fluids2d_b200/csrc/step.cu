@@ -57,7 +57,7 @@ static dim3 blk2d() {
 }
 static dim3 grd2d(const f2d_ctx *c) { dim3 b = blk2d(); return dim3((c->n1 + b.x - 1) / b.x, (c->n2 + b.y - 1) / b.y); }
 
-enum { M_EULER = 0, M_BOUSS = 1, M_RSW = 2, M_QGRSW = 3 };
+enum { M_EULER = 0, M_BOUSS = 1, M_RSW = 2, M_QGRSW = 3, M_VADV = 4 };
 
 // ---------------------------------------------------------------------------
 // momentum tendency:  addvortexforce (operators.py:6-13, weno.py:367-385)
@@ -522,6 +522,80 @@ k_qg_back(Grid g, const double *__restrict__ psi, const int8_t *__restrict__ msk
     if (i <= g.n1 - 2) duy[k_out] = (psi[k + 1] - psi[k]) * (double)msky[k];
 }
 
+// ---------------------------------------------------------------------------
+// glue of the stream-function models (eulerpsi, qg) and of vectoradv
+// ---------------------------------------------------------------------------
+// centerstovertices (operators.py:126-133): v[1:,1:] = 1/4 sum4((a - sub*hb)) ; v *= mskv
+__global__ void __launch_bounds__(256)
+k_c2v(Grid g, const double *__restrict__ a, const double *__restrict__ hb, double sub,
+      const int8_t *__restrict__ mskv, double *__restrict__ v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.n1 || j >= g.n2) return;
+    long k = (long)j * g.n1 + i;
+    const long s1 = g.n1;
+    double r = v[k];                      // row 0 / column 0 keep their value (times mskv)
+    if (i >= 1 && j >= 1) {
+        auto A = [&](long m) { return a[m] - hb[m] * sub; };
+        r = 0.25 * (((A(k - s1 - 1) + A(k - 1)) + A(k - s1)) + A(k));
+    }
+    v[k] = r * (double)mskv[k];
+}
+
+// perpgrad (operators.py:144-149) with the contravariant scaling, then fill
+__global__ void __launch_bounds__(256)
+k_perpgrad(Grid g, const double *__restrict__ psi, const int8_t *__restrict__ mskx,
+           const int8_t *__restrict__ msky, double sx, double sy, double *__restrict__ ux,
+           double *__restrict__ uy) {
+    THREAD_2D(g);
+    double vx = ux[k], vy = uy[k];
+    if (j <= g.n2 - 2) vx = -(psi[k + s1] - psi[k]) * (double)mskx[k];
+    if (i <= g.n1 - 2) vy = (psi[k + 1] - psi[k]) * (double)msky[k];
+    ux[k_out] = vx * sx;
+    uy[k_out] = vy * sy;
+}
+
+// vectoradv diag (equations.py:181-185): omega = curl(v) * slip ; q = 2 * ke(v, U) ; fill
+template <int MK>
+__global__ void __launch_bounds__(256)
+k_vadv_diag(Grid g, const double *__restrict__ vx, const double *__restrict__ vy,
+            const double *__restrict__ Ux, const double *__restrict__ Uy,
+            const int8_t *__restrict__ msk, const int8_t *__restrict__ slip,
+            const int8_t *__restrict__ okx, const int8_t *__restrict__ oky,
+            double *__restrict__ omega, double *__restrict__ q) {
+    THREAD_2D(g);
+    double om = 0;
+    if (j >= 1) om = -(vx[k] - vx[k - s1]);
+    if (i >= 1) om += vy[k] - vy[k - 1];
+    omega[k_out] = om * (double)slip[k];
+    double e = 0;
+    if (MK == F2D_METHOD_CLASSIC) {
+        if (i <= g.n1 - 2) e = vx[k + 1] * Ux[k + 1] + vx[k] * Ux[k];
+        if (j <= g.n2 - 2) e += vy[k + s1] * Uy[k + s1] + vy[k] * Uy[k];
+        e *= (double)msk[k] * 0.25;
+    } else {
+        constexpr int M = MK > 3 ? 0 : MK;
+        int ox = okx[k];
+        if (ox > 0) {
+            double Um = 0.5 * (Ux[k] + Ux[k + 1]);
+            double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = vx[k], w3 = vx[k + 1];
+            if (ox > 2) { w1 = vx[k - 1]; w4 = vx[k + 2]; }
+            if (ox > 4) { w0 = vx[k - 2]; w5 = vx[k + 3]; }
+            e += recon<M>(ox, Um, w0, w1, w2, w3, w4, w5) * Um;
+        }
+        int oy = oky[k];
+        if (oy > 0) {
+            double Um = 0.5 * (Uy[k] + Uy[k + s1]);
+            double w0 = 0, w1 = 0, w4 = 0, w5 = 0, w2 = vy[k], w3 = vy[k + s1];
+            if (oy > 2) { w1 = vy[k - s1]; w4 = vy[k + 2 * s1]; }
+            if (oy > 4) { w0 = vy[k - 2 * s1]; w5 = vy[k + 3 * s1]; }
+            e += recon<M>(oy, Um, w0, w1, w2, w3, w4, w5) * Um;
+        }
+        e *= (double)msk[k] * 0.5;
+    }
+    q[k_out] = e * 2;
+}
+
 // Model.set_dt (model.py:85): max|U.x|, max|U.y|
 __global__ void __launch_bounds__(256)
 k_maxabs(long n, const double *__restrict__ ux, const double *__restrict__ uy, double idx2,
@@ -548,10 +622,14 @@ static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy, RkFuse rk = RkFu
     Grid g = grid_of(c);
     const double *p = c->has("p") ? c->f("p") : nullptr;
     const double *b = c->has("b") ? c->f("b") : nullptr;
-    const double *ke = c->f("ke");
+    // vectoradv (equations.py:175-179): the advecting velocity is state.U itself, `q` plays ke
+    const bool vadv = MODEL == M_VADV;
+    if (vadv) g.idx2 = g.idy2 = 1.0;
+    const double *ke = vadv ? c->f("q") : c->f("ke");
+    const double *ax = vadv ? c->f("U.x") : c->f("u.x"), *ay = vadv ? c->f("U.y") : c->f("u.y");
     double fcor = c->cfg.f0 * c->area * 0.25;
     double halfdy = 0.5 * c->dy;
-#define RHS_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), ke, p, b, c->m("ov.x"), c->m("ov.y"), \
+#define RHS_ARGS g, ax, ay, c->f("omega"), ke, p, b, c->m("ov.x"), c->m("ov.y"), \
                  c->m("mskx"), c->m("msky"), fcor, halfdy, dux, duy, rk
     switch (c->cfg.vortexforce) {
     case F2D_METHOD_WENO: k_rhs_mom<WENO, MODEL, NC><<<grd2d(c), blk2d(), 0, c->stream>>>(RHS_ARGS); break;
@@ -565,10 +643,14 @@ static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy, RkFuse rk = RkFu
     return F2D_OK;
 }
 
-static int launch_divflux(f2d_ctx *c, const double *q, double *dq) {
+// direct_U: the model's transport velocity IS the contravariant state.U
+// (eulerpsi, qg, advection), not sharp(u)
+static int launch_divflux(f2d_ctx *c, const double *q, double *dq, bool direct_U = false) {
     Grid g = grid_of(c);
+    if (direct_U) g.idx2 = g.idy2 = 1.0;
+    const double *vx = direct_U ? c->f("U.x") : c->f("u.x"), *vy = direct_U ? c->f("U.y") : c->f("u.y");
     double *fx = c->f("flx.x"), *fy = c->f("flx.y");
-#define FLX_ARGS g, c->f("u.x"), c->f("u.y"), q, c->m("oc.x"), c->m("oc.y"), fx, fy
+#define FLX_ARGS g, vx, vy, q, c->m("oc.x"), c->m("oc.y"), fx, fy
     switch (c->cfg.compflux) {
     case F2D_METHOD_WENO: k_flux<WENO><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
     case F2D_METHOD_UPWIND: k_flux<UPWIND><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
@@ -634,8 +716,16 @@ static std::string dsname(int k, const char *leaf) { return "ds" + std::to_strin
 int model_rhs(f2d_ctx *c, int k) {
     if (!c->mesh_ready) { set_error("f2d_rhs before f2d_set_mask"); return F2D_ERR_STATE; }
     if (k < 0 || k >= c->nstages) { set_error("stage %d out of range", k); return F2D_ERR_ARG; }
-    double *dux = c->f(dsname(k, "u.x")), *duy = c->f(dsname(k, "u.y"));
     Grid g = grid_of(c);
+    switch (c->cfg.model) {     // the scalar-transport models have no momentum tendency
+    case F2D_MODEL_EULERPSI: return launch_divflux(c, c->f("omega"), c->f(dsname(k, "omega")), true);
+    case F2D_MODEL_QG: return launch_divflux(c, c->f("pv"), c->f(dsname(k, "pv")), true);
+    case F2D_MODEL_ADVECTION: return launch_divflux(c, c->f("q"), c->f(dsname(k, "q")), true);
+    case F2D_MODEL_VECTORADV:
+        return launch_rhs_mom<M_VADV>(c, c->f(dsname(k, "v.x")), c->f(dsname(k, "v.y")));
+    default: break;
+    }
+    double *dux = c->f(dsname(k, "u.x")), *duy = c->f(dsname(k, "u.y"));
     switch (c->cfg.model) {
     case F2D_MODEL_EULER:
         return launch_rhs_mom<M_EULER>(c, dux, duy);
@@ -770,6 +860,40 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         return launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct);
     case F2D_MODEL_QGRSW:
         return launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1);
+    case F2D_MODEL_ADVECTION:
+        return F2D_OK;                                   // equations.py:167-168
+    case F2D_MODEL_EULERPSI:                             // equations.py:81-85
+    case F2D_MODEL_QG: {                                 // equations.py:98-101, operators.py:186-191
+        const bool qg = c->cfg.model == F2D_MODEL_QG;
+        if (qg && c->cfg.reserved[4]) { set_error("qg with beta != 0 (mesh.f) is not on the device path"); return F2D_ERR_UNSUPPORTED; }
+        double *rhs = c->f(qg ? "work" : "vomega");
+        k_c2v<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f(qg ? "pv" : "omega"), c->hb, qg ? c->cfg.f0 / +c->cfg.H : 0.0,
+                                                     c->m("mskv"), rhs);
+        LAUNCH_CHECK(c);
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi")));
+        F2D_TRY(mg_solve(c, qg ? F2D_SOLVER_HELMHOLTZ : F2D_SOLVER_VERTICES, rhs, 1.0, c->f("psi"), nullptr, nullptr));
+        F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
+        // perpgrad(..., contravariant=True): u.x *= 1/dy**2, u.y *= 1/dx**2
+        k_perpgrad<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("mskx"), c->m("msky"), c->idy2, c->idx2,
+                                                          c->f("U.x"), c->f("U.y"));
+        LAUNCH_CHECK(c);
+        return F2D_OK;
+    }
+    case F2D_MODEL_VECTORADV: {                          // equations.py:181-185
+#define VD_ARGS g, c->f("v.x"), c->f("v.y"), c->f("U.x"), c->f("U.y"), c->m("msk"), c->m("slip"), c->m("ok.x"), c->m("ok.y"), \
+                c->f("omega"), c->f("q")
+        switch (c->cfg.innerproduct) {
+        case F2D_METHOD_WENO: k_vadv_diag<0><<<grd2d(c), blk2d(), 0, c->stream>>>(VD_ARGS); break;
+        case F2D_METHOD_UPWIND: k_vadv_diag<1><<<grd2d(c), blk2d(), 0, c->stream>>>(VD_ARGS); break;
+        case F2D_METHOD_CENTERED: k_vadv_diag<2><<<grd2d(c), blk2d(), 0, c->stream>>>(VD_ARGS); break;
+        case F2D_METHOD_CWENO: k_vadv_diag<3><<<grd2d(c), blk2d(), 0, c->stream>>>(VD_ARGS); break;
+        case F2D_METHOD_CLASSIC: k_vadv_diag<4><<<grd2d(c), blk2d(), 0, c->stream>>>(VD_ARGS); break;
+        default: set_error("bad innerproduct method"); return F2D_ERR_ARG;
+        }
+#undef VD_ARGS
+        LAUNCH_CHECK(c);
+        return F2D_OK;
+    }
     }
     set_error("unknown model %d", c->cfg.model);
     return F2D_ERR_ARG;
@@ -889,8 +1013,10 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
 
 int max_abs_U(f2d_ctx *c, double *out) {
     int nb = c->nsm * 8;
-    k_maxabs<<<nb, 256, 0, c->stream>>>((long)c->n, c->f("u.x"), c->f("u.y"), c->idx2, c->idy2,
-                                        c->d_part, c->d_count, c->d_scal + 12);
+    // models that carry the covariant u derive U = sharp(u); the others hold U itself
+    const bool cov = c->has("u.x");
+    k_maxabs<<<nb, 256, 0, c->stream>>>((long)c->n, c->f(cov ? "u.x" : "U.x"), c->f(cov ? "u.y" : "U.y"),
+                                        cov ? c->idx2 : 1.0, cov ? c->idy2 : 1.0, c->d_part, c->d_count, c->d_scal + 12);
     F2D_CUDA(cudaMemcpyAsync(c->d_scal + 8, c->d_scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     LAUNCH_CHECK(c);
     F2D_TRY(dist_allreduce(c, c->d_scal + 8, 2, true));

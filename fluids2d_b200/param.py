@@ -8,7 +8,7 @@ _methods_extended = _methods + ["classic"]
 _integrators = ["rk3", "ef", "enrk3", "LFRA"]
 
 # models whose time step runs on the device in this build
-DEVICE_MODELS = ["euler", "boussinesq", "rsw", "qgrsw"]
+DEVICE_MODELS = ["euler", "boussinesq", "rsw", "qgrsw", "eulerpsi", "qg", "advection", "vectoradv"]
 
 
 class Param:

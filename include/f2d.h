@@ -39,7 +39,8 @@ typedef enum {
 } f2d_status;
 
 /* param.py:1-7 string enums, in the order the reference lists them */
-enum { F2D_MODEL_EULER = 0, F2D_MODEL_BOUSSINESQ = 1, F2D_MODEL_RSW = 2, F2D_MODEL_QGRSW = 3 };
+enum { F2D_MODEL_EULER = 0, F2D_MODEL_BOUSSINESQ = 1, F2D_MODEL_RSW = 2, F2D_MODEL_QGRSW = 3,
+       F2D_MODEL_EULERPSI = 4, F2D_MODEL_QG = 5, F2D_MODEL_ADVECTION = 6, F2D_MODEL_VECTORADV = 7 };
 enum { F2D_METHOD_WENO = 0, F2D_METHOD_UPWIND = 1, F2D_METHOD_CENTERED = 2, F2D_METHOD_CWENO = 3,
        F2D_METHOD_CLASSIC = 4 /* innerproduct only, operators.py:86-89 */ };
 enum { F2D_INT_RK3 = 0, F2D_INT_EF = 1, F2D_INT_ENRK3 = 2 };
@@ -68,6 +69,7 @@ typedef struct {
     int32_t solver_kind;    /* 0 MG-preconditioned CG, 1 plain V-cycles      */
     int32_t nu1, nu2;       /* red-black sweeps before / after; 0 -> 2       */
     int32_t reserved[8];    /* [1], [2], [3]: slab decomposition, see f2d_dist_init;
+                             * [4]: non-zero when param.beta != 0 (qg: unsupported);
                              * [0]: 1 + order of the first-guess extrapolation across
                              * time steps for the solves inside f2d_step (0 = default
                              * = quadratic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic) */
@@ -98,7 +100,8 @@ int f2d_get_mesh_array(f2d_ctx *ctx, const char *name, int8_t *h_out);
 int f2d_set_topography(f2d_ctx *ctx, const double *h_hb);
 
 /* ---- State (states.py:37-79).  Field names: "u.x","u.y","U.x","U.y","omega",
- *      "ke","p","div","flx.x","flx.y","b","h","pv","psi"; scratch tendencies
+ *      "ke","p","div","flx.x","flx.y","b","h","pv","psi","vomega","work","q","v.x","v.y";
+ *      scratch tendencies
  *      "ds0.u.x", "ds1.h", ... (integrators.py:66-67) ----------------------- */
 int f2d_upload(f2d_ctx *ctx, const char *field, const double *h_src);
 int f2d_download(f2d_ctx *ctx, const char *field, double *h_dst);

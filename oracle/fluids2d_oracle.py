@@ -432,6 +432,10 @@ SPECS = {
     "boussinesq": (("b", "u", "U", "omega", "ke", "p", "div", "flx"), ("b", "u")),
     "rsw": (("u", "h", "U", "omega", "ke", "p", "flx", "pv"), ("u", "h")),
     "qgrsw": (("u", "h", "U", "omega", "ke", "p", "flx", "pv", "psi"), ("u", "h")),
+    "eulerpsi": (("omega", "U", "psi", "vomega", "flx"), ("omega",)),
+    "qg": (("pv", "U", "h", "flx", "work", "psi"), ("pv",)),
+    "advection": (("q", "U", "flx"), ("q",)),
+    "vectoradv": (("v", "U", "omega", "q"), ("v",)),
 }
 VECTORS = ("u", "U", "flx", "v")
 
@@ -501,6 +505,49 @@ def rhs_and_diag(param, mesh):
             sharp(mesh, s.u, s.U)
             compute_vorticity(mesh, s.u, s.omega)
             fill(s.omega)
+    elif model == "eulerpsi":                            # equations.py:73-86
+        def rhs(s, ds):
+            divflux(param, mesh, s.flx, s.omega, s.U, ds.omega)
+            fill(ds.omega)
+
+        def diag(s):
+            centerstovertices(mesh, s.omega, s.vomega)
+            mesh.poisson_vertices.solve(s.vomega, s.psi)
+            perpgrad(mesh, s.psi, s.U, contravariant=True)
+            fill(s.U)
+
+    elif model == "qg":                                  # equations.py:89-103, operators.py:186-191
+        def rhs(s, ds):
+            divflux(param, mesh, s.flx, s.pv, s.U, ds.pv)
+            fill(ds.pv)
+
+        def diag(s):
+            pvback = mesh.hb * mesh.qgcoef
+            centerstovertices(mesh, s.pv - pvback, s.work)
+            if param.beta != 0:
+                raise NotImplementedError("qg with beta needs the user-set mesh.f")
+            mesh.qg_helmholtz.solve(s.work, s.psi)
+            perpgrad(mesh, s.psi, s.U, contravariant=True)
+
+    elif model == "advection":                           # equations.py:160-170
+        def rhs(s, ds):
+            divflux(param, mesh, s.flx, s.q, s.U, ds.q)
+            fill(ds.q)
+
+        def diag(s):
+            pass
+
+    elif model == "vectoradv":                           # equations.py:173-187
+        def rhs(s, ds):
+            addvortexforce(param, mesh, s.U, s.omega, ds.v)
+            addgrad(mesh, s.q, ds.v)
+            fill(ds.v)
+
+        def diag(s):
+            compute_vorticity(mesh, s.v, s.omega)
+            compute_kinetic_energy(param, mesh, s.v, s.U, s.q)
+            s.q[:] *= 2
+            fill(s.omega); fill(s.q)
     else:
         raise NotImplementedError(model)
     return rhs, diag

@@ -233,6 +233,79 @@ def case_lock_exchange():
     run_case("lock_exchange", kw, ic=lock_ic)
 
 
+# ---- the scalar-transport / stream-function models ----------
+def case_advection():
+    # tests/test_models.py:17-26 set-up (body rotation + checkerboard tracer)
+    def ic(model):
+        mesh = model.mesh
+        omega = (4 * np.pi / 100) * np.ones(mesh.shape) * mesh.mskv
+        f2d.tools.set_uv_from_omega(model, omega, model.state.U)
+        x, y = mesh.xy("c")
+        q = model.state.q
+        q[:, :] = (np.round(x * 8) % 2 + np.round(y * 8) % 2) / 2
+        q *= mesh.msk
+    run_case("advection", dict(model="advection"), ic=ic)
+
+
+def case_advection_disc_upwind():
+    def mask(model):
+        x, y = model.mesh.xy()
+        model.mesh.msk[(x - 0.5) ** 2 + (y - 0.5) ** 2 > 0.47 ** 2] = 0
+
+    def ic(model):
+        mesh = model.mesh
+        x, y = mesh.xy("v")
+        omega = (gaussian(x, y, 0.4, 0.5, 0.08) - gaussian(x, y, 0.6, 0.5, 0.08)) * mesh.mskv
+        f2d.tools.set_uv_from_omega(model, omega, model.state.U)
+        xc, yc = mesh.xy("c")
+        model.state.q[:, :] = gaussian(xc, yc, 0.5, 0.65, 0.1) * mesh.msk
+    run_case("advection_disc_upwind", dict(model="advection", nx=56, ny=48, compflux="upwind", maxorder=4),
+             mask_fn=mask, ic=ic)
+
+
+def case_eulerpsi():
+    # vortex.py:22-25 (eulerpsi branch): vorticity at cell centres
+    def ic(model):
+        x, y = model.mesh.xy("c")
+        om = model.state.omega
+        om[:, :] = gaussian(x, y, 1.05, 0.5, 0.05) - gaussian(x, y, 0.95, 0.5, 0.05)
+        om *= model.mesh.msk * model.mesh.area
+        model.integrator.diag(model.state)
+    run_case("eulerpsi", dict(model="eulerpsi", Lx=2.0, ny=50, nx=100, dt=0.4), ic=ic)
+
+
+def case_qg():
+    # geos_adj.py:12-49 with model = "qg"
+    def ic(model):
+        mesh = model.mesh
+        x, y = mesh.xy("c")
+        h = model.state.h
+        h[:] = model.param.H + 0.2 * (gaussian(x, y, 0.6, 0.5, 0.1) - gaussian(x, y, 0.4, 0.5, 0.1))
+        h *= (mesh.msk * mesh.area)
+        s = model.state
+        qg_projection(mesh, s.U, s.h, s.pv, s.psi)
+        model.integrator.diag(model.state)
+    run_case("qg", dict(model="qg", nx=64, ny=56, dtmax=1, f0=10.0), mask_fn=island_mask, ic=ic)
+
+
+def case_vectoradv():
+    # src/experiments/vector_advection.py:10-30, 66-76 (disc domain, body rotation)
+    def mask(model):
+        x, y = model.mesh.xy()
+        model.mesh.msk[(x - 0.5) ** 2 + (y - 0.5) ** 2 > 0.5 ** 2] = 0
+
+    def ic(model):
+        mesh = model.mesh
+        omega = (4 * np.pi / 100) * np.ones(mesh.shape) * mesh.mskv
+        f2d.tools.set_uv_from_omega(model, omega, model.state.U)
+        x, y = mesh.xy("x")
+        vx = model.state.v.x
+        vx[:, :] = gaussian(x, y, 0.7, 0.5, 0.05)
+        vx *= mesh.mskx
+        model.integrator.diag(model.state)
+    run_case("vectoradv", dict(model="vectoradv", nx=50, ny=50), mask_fn=mask, ic=ic)
+
+
 def run_to_tend():
     """tests/test_models.py:9-15: default 40x40 Euler dipole, model.run() to
     tend = 10 with the adaptive CFL step.  The reference's own assertion
@@ -388,7 +461,8 @@ if __name__ == "__main__":
     todo = [case_euler40, case_vortex, case_vortex_triangle, case_disc_island, case_xper_noslip,
             case_euler_enrk3_upwind, case_euler_centered_ef, case_euler_cweno,
             case_rsw, case_rsw_islands, case_qgrsw_topo, case_qgrsw_islands,
-            case_warm_bubble, case_lock_exchange, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
+            case_warm_bubble, case_lock_exchange, case_advection, case_advection_disc_upwind, case_eulerpsi,
+            case_qg, case_vectoradv, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
     for fn in todo:
         if which is None or fn.__name__ in which:
             fn()

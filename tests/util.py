@@ -9,7 +9,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 EULER_CASES = ["euler40", "vortex", "vortex_triangle", "disc_island", "xper_noslip",
                "euler_enrk3_upwind", "euler_centered_ef", "euler_cweno"]
 ALL_CASES = EULER_CASES + ["rsw", "rsw_islands", "qgrsw_topo", "qgrsw_islands",
-                           "warm_bubble", "lock_exchange"]
+                           "warm_bubble", "lock_exchange",
+                           # the remaining models on the same kernels
+                           "advection", "advection_disc_upwind", "eulerpsi", "qg", "vectoradv"]
 
 
 class Golden:
@@ -88,7 +90,7 @@ def field_mask(mesh, name):
         return mesh.mskx
     if name.endswith(".y"):
         return mesh.msky
-    if base in ("omega", "pv", "psi"):
+    if base in ("omega", "pv", "psi", "vomega", "work"):
         return mesh.mskv
     return mesh.msk
 
