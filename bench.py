@@ -248,9 +248,16 @@ def run_ours(args):
                          "frac": round(kbytes / (kms * 1e-3) / 1e9 / peak, 3) if kbytes else None}
     dom = eng.dominant_kernel()
     roof = None
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and n == 4096:
+        with open(tpath) as f:
+            traffic = json.load(f)      # DRAM bytes per launch from the committed ncu --set full capture
+    for k, v in kernels.items():
+        v["traffic"] = traffic.get(k)
     if kernels:
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
                 "kernels": kernels}
 
     out = None
@@ -318,12 +325,12 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096, help="grid size (default: the headline 4096)")
+    ap.add_argument("--grid", dest="n", type=int, default=4096, help="grid size n (default: the headline 4096)")
     ap.add_argument("--cpu-n", type=int, default=512, help="grid of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N > 1: split the n x n grid instead of growing it with N")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent copies instead of one decomposed grid")
-    ap.add_argument("--nu", type=int, default=2, help="smoothing sweeps per V-cycle leg")
+    ap.add_argument("--sweeps", dest="nu", type=int, default=2, help="smoothing sweeps per V-cycle leg")
     ap.add_argument("--guess", type=int, default=3, help="first-guess extrapolation order (0 off)")
     ap.add_argument("--rtol", type=float, default=1e-12, help="elliptic solver tolerance")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline timings")

@@ -175,6 +175,11 @@ int f2d_sync(f2d_ctx *c) {
 int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
     NEED(c, "null ctx");
     F2D_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->dist.on) {   // neighbours map my arrays: unmap everywhere before anything is freed
+        p2p_teardown(c);
+        F2D_TRY(dist_allreduce(c, c->d_scal + 26, 1, false));
+        F2D_CUDA(cudaStreamSynchronize(c->stream));
+    }
     F2D_TRY(build_mesh(c, h_msk));
     for (auto &G : c->guess) G.valid = 0;     // a new mask invalidates the solve history
     // meshes.py:39-47
@@ -182,6 +187,27 @@ int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
     F2D_TRY(mg_build(c, F2D_SOLVER_VERTICES));
     if (c->cfg.model == F2D_MODEL_RSW || c->cfg.model == F2D_MODEL_QGRSW || c->cfg.model == F2D_MODEL_QG)
         F2D_TRY(mg_build(c, F2D_SOLVER_HELMHOLTZ));
+    if (c->dist.on) {
+        // every array the time loop exchanges, in the same order on every rank
+        std::vector<void *> arr;
+        std::vector<long long> rows, pad, rb;
+        auto add = [&](void *p, long long r, long long pd, long long b) { if (p) { arr.push_back(p); rows.push_back(r); pad.push_back(pd); rb.push_back(b); } };
+        const long long fb = (long long)c->n1 * sizeof(double);
+        for (auto &kv : c->fields) add(kv.second, c->n2, 0, fb);
+        add(c->tmp[0], c->n2, 0, fb);
+        add(c->tmp[1], c->n2, 0, fb);
+        for (int w = 0; w < 3; w++) {
+            Multigrid &M = c->mg[w];
+            if (!M.built) continue;
+            for (double *p : {M.r, M.z, M.p, M.p2, M.q}) add(p, c->n2, 0, fb);
+            for (float *p : {M.zf, M.zf2}) add(p, c->n2, 0, (long long)c->n1 * sizeof(float));
+            for (size_t l = 1; l < M.lev.size(); l++) {
+                Level &L = M.lev[l];
+                for (CT *p : {L.x, L.x2, L.b}) add(p, L.ny + 2, 1, (long long)L.pitch * sizeof(CT));
+            }
+        }
+        F2D_TRY(p2p_setup(c, arr, rows, pad, rb));
+    }
     return F2D_OK;
 }
 

@@ -90,6 +90,13 @@ struct Dist {
     ncclComm_t comm = nullptr;
     int G = 8;                       // ghost rows at an interface
     bool south = false, north = false;
+    // peer-to-peer exchange (dist.cu): neighbours' arrays mapped through CUDA IPC
+    bool p2p = false;
+    unsigned long long *flags = nullptr;
+    struct Geo { long long rows_total, pad, row_bytes; };
+    std::vector<void *> peer_south, peer_north;      // index 0 = the flag block
+    std::vector<Geo> rec_south, rec_north;
+    std::map<const void *, int> index;               // my array -> slot
 };
 
 struct Multigrid {
@@ -189,6 +196,10 @@ int dist_allgather_rows(f2d_ctx *c, const void *src_rows, void *dst, size_t byte
 int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id);
 int dist_unique_id(char *out);
 void dist_free(f2d_ctx *c);
+int p2p_setup(f2d_ctx *c, const std::vector<void *> &arrays, const std::vector<long long> &rows_total,
+              const std::vector<long long> &pad, const std::vector<long long> &row_bytes);
+void p2p_teardown(f2d_ctx *c);
+int p2p_check(f2d_ctx *c);
 int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
 int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes);
 }  // namespace f2d

@@ -1582,7 +1582,10 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     c->max_relres = std::max(c->max_relres, relres);
     if (iters_out) *iters_out = it;
     if (relres_out) *relres_out = relres;
-    if (c->dist.on) F2D_TRY(exchange_fine(c, M, x));
+    if (c->dist.on) {
+        F2D_TRY(exchange_fine(c, M, x));
+        F2D_TRY(p2p_check(c));
+    }
     F2D_TRY(op_fill(c, x));
     if (!conv || !std::isfinite(relres)) {
         set_error("elliptic solve %d: relative residual %.3e after %d iterations (rtol %.1e)", which,

@@ -1,4 +1,4 @@
-for args in "--guess 0" "--guess 1" "--guess 2" "--guess 3" "--guess 2 --nu 1" "--guess 2 --nu 3"; do
+for args in "--guess 0" "--guess 1" "--guess 2" "--guess 3" "--guess 2 --sweeps 1" "--guess 2 --sweeps 3"; do
 python bench.py --steps 6 --warmup 4 --no-cpu --no-kernels $args > /tmp/b.json 2>/tmp/b.err || tail -3 /tmp/b.err
 python - "$args" <<'PY'
 import json,sys
