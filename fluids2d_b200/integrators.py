@@ -110,9 +110,17 @@ class RKIntegrator:
         self.engine.diag()
         self.download(s)
 
+    def _step_inputs(self, state):
+        """fields a step READS before it writes them: everything except the pure
+        outputs / work arrays (U = sharp(u) where the model carries u, div, flx,
+        vomega, work), which need not cross PCIe on the way in"""
+        has_u = "u" in state._fields or "uh" in state._fields
+        skip = {"div", "flx.x", "flx.y", "vomega", "work"} | ({"U.x", "U.y"} if has_u else set())
+        return [n for n in self._names(state) if n not in skip]
+
     def step(self, state, time):
         if self.rhs is self._device_rhs:
-            self.upload(state)
+            self.upload(state, self._step_inputs(state))
             self.engine.step(time.dt, 1)
             self.download(state)
         else:
