@@ -15,7 +15,7 @@ from . import build as _build
 MODELS = {"euler": 0, "boussinesq": 1, "rsw": 2, "qgrsw": 3, "eulerpsi": 4, "qg": 5, "advection": 6,
           "vectoradv": 7}
 METHODS = {"weno": 0, "upwind": 1, "centered": 2, "cweno": 3, "classic": 4}
-INTEGRATORS = {"rk3": 0, "ef": 1, "enrk3": 2}
+INTEGRATORS = {"rk3": 0, "ef": 1, "enrk3": 2, "LFRA": 3}
 SOLVERS = {"c": 0, "v": 1, "h": 2}
 NOSLIP = {"left": 1, "right": 2, "bottom": 4, "top": 8}
 NOSLIP_ALL = 16
@@ -62,6 +62,7 @@ SIGNATURES = {
     "f2d_download": (_I, [_P, C.c_char_p, _P]),
     "f2d_field_ptr": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
     "f2d_step": (_I, [_P, _D, _I]),
+    "f2d_step_lfra": (_I, [_P, _D, _I, _D]),
     "f2d_rhs": (_I, [_P, _I]),
     "f2d_addto": (_I, [_P, _I, C.POINTER(_D)]),
     "f2d_diag": (_I, [_P]),
@@ -268,6 +269,9 @@ class Engine:
     # -- stepping -----------------------------------------------------------
     def step(self, dt, nsteps=1):
         self._chk(self.lib.f2d_step(self._h, float(dt), int(nsteps)))
+
+    def step_lfra(self, dt, first, gamma):
+        self._chk(self.lib.f2d_step_lfra(self._h, float(dt), int(bool(first)), float(gamma)))
 
     def rhs(self, k):
         self._chk(self.lib.f2d_rhs(self._h, int(k)))

@@ -50,7 +50,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     NEED(cfg->nh == 3, "halowidth must be 3 (the widest stencil reaches 3 cells, weno.py:353-355)");
     NEED(cfg->nx >= 2 * cfg->nh && cfg->ny >= 2 * cfg->nh, "nx, ny must be >= 2*halowidth");
     NEED(cfg->model >= 0 && cfg->model <= F2D_MODEL_VECTORADV, "unknown model %d", cfg->model);
-    NEED(cfg->integrator >= 0 && cfg->integrator <= F2D_INT_ENRK3, "unknown integrator %d", cfg->integrator);
+    NEED(cfg->integrator >= 0 && cfg->integrator <= F2D_INT_LFRA, "unknown integrator %d", cfg->integrator);
     NEED(cfg->maxorder == 2 || cfg->maxorder == 4 || cfg->maxorder == 6, "maxorder must be 2, 4 or 6");
     NEED(cfg->vortexforce >= 0 && cfg->vortexforce <= 3, "unknown vortexforce method");
     NEED(cfg->compflux >= 0 && cfg->compflux <= 3, "unknown compflux method");
@@ -260,6 +260,10 @@ int f2d_field_ptr(f2d_ctx *c, const char *field, double **d_ptr) {
 int f2d_step(f2d_ctx *c, double dt, int nsteps) {
     NEED(c, "null ctx");
     return model_step(c, dt, nsteps);
+}
+int f2d_step_lfra(f2d_ctx *c, double dt, int first, double gamma) {
+    NEED(c, "null ctx");
+    return model_step_lfra(c, dt, first, gamma);
 }
 int f2d_rhs(f2d_ctx *c, int k) {
     NEED(c, "null ctx");

@@ -179,6 +179,7 @@ int model_rhs(f2d_ctx *c, int k);
 int model_addto(f2d_ctx *c, int ncoef, const double *coefs);
 int model_diag(f2d_ctx *c);
 int model_step(f2d_ctx *c, double dt, int nsteps);
+int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma);
 int max_abs_U(f2d_ctx *c, double *out);
 // mg.cu
 int mg_build(f2d_ctx *c, int which);

@@ -989,8 +989,51 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     return model_diag_impl(c, true);
 }
 
+// ---------------------------------------------------------------------------
+// Leap-frog + Robert-Asselin filter (integrators.py:20-53).  scratch = [sb, sa, ds]
+//   first:  sb = s ; sa = s ; s += dt ds
+//   else:   sa += 2 dt ds ; s += (gamma sa + gamma sb) - 2 gamma s ; (sa, s, sb) <- (s, sa, s)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lfra(long n, double *__restrict__ s, double *__restrict__ sb, double *__restrict__ sa,
+       const double *__restrict__ ds, double dt, double gamma, int first) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double sv = s[k], d = ds[k];
+    if (first) {
+        sb[k] = sv;
+        sa[k] = sv;
+        s[k] = sv + dt * d;
+    } else {
+        double san = sa[k] + (2 * dt) * d;
+        double acc = gamma * san;
+        acc = acc + gamma * sb[k];
+        acc = acc + (-2 * gamma) * sv;
+        double sf = sv + acc;
+        sb[k] = sf;        // rightpermute(sa, s, sb): sb <- s, s <- sa, sa <- sb
+        s[k] = san;
+        sa[k] = sf;
+    }
+}
+
+int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma) {
+    if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
+    if (c->cfg.integrator != F2D_INT_LFRA) { set_error("context was not created with the LFRA integrator"); return F2D_ERR_STATE; }
+    if (c->dist.on) { set_error("LFRA is not available in slab mode"); return F2D_ERR_UNSUPPORTED; }
+    F2D_TRY(model_rhs(c, 2));
+    long n = (long)c->n;
+    unsigned grd = (unsigned)((n + 255) / 256);
+    for (const std::string &leaf : c->prognostic) {
+        k_lfra<<<grd, 256, 0, c->stream>>>(n, c->f(leaf), c->f(dsname(0, leaf.c_str())), c->f(dsname(1, leaf.c_str())),
+                                           c->f(dsname(2, leaf.c_str())), dt, gamma, first);
+        LAUNCH_CHECK(c);
+    }
+    return model_diag(c);
+}
+
 int model_step(f2d_ctx *c, double dt, int nsteps) {
     if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
+    if (c->cfg.integrator == F2D_INT_LFRA) { set_error("LFRA steps go through f2d_step_lfra"); return F2D_ERR_STATE; }
     for (int it = 0; it < nsteps; it++) {
         for (int s = 0; s < c->nstages; s++) {
             double co[3];

@@ -25,6 +25,8 @@ _specs = namedtuple("specs", ("caller", "nstages"))
 def get_integrator(param, mesh, state):
     if param.integrator in RKintegrators:
         return RKIntegrator(param, mesh, state)
+    if param.integrator == "LFRA":
+        return LFRAintegrator(param, mesh, state)
     raise NotImplementedError(f"{param.integrator} is not implemented on the device path")
 
 
@@ -145,6 +147,46 @@ class RKIntegrator:
             e.addto(coefs)
             e.diag()
             self.download(state)
+
+
+class LFRAintegrator(RKIntegrator):
+    """Leap-Frog integrator combined with a Robert-Asselin filter; the first
+    iteration is an Euler forward step (integrators.py:20-53).
+    ``scratch = [sb, sa, ds]`` as in the reference; scripts that edit it
+    (tracer_advection.fliptime) see and set the host copies."""
+
+    def __init__(self, param, mesh, state):
+        self.param, self.mesh = param, mesh
+        self.engine = mesh.engine
+        self.name = "LFRA"
+        self.scratch = [Prognostic(param, mesh.shape) for _ in range(3)]
+        self.RAgamma = param.RAgamma
+        self._prognostic = type(self.scratch[0])._fields
+        self._device_rhs = self._rhs_on_device
+        self.rhs = self._device_rhs
+        self.diag = self._diag_on_device
+        self._fields = None
+
+    def _scratch_io(self, upload):
+        e = self.engine
+        for k in (0, 1):      # sb, sa carry the leap-frog history
+            for n, a in leaves(self.scratch[k]):
+                (e.upload_async if upload else e.download_async)(f"ds{k}.{n}", a)
+        e.sync()
+
+    def step(self, state, time):
+        if self.rhs is not self._device_rhs:
+            raise NotImplementedError("host forcing with the LFRA integrator is not on the device path")
+        self.upload(state, self._step_inputs(state))
+        self._scratch_io(True)
+        self.engine.step_lfra(time.dt, time.ite == 0, self.RAgamma)
+        self.download(state)
+        self._scratch_io(False)
+        time.pushforward()
+
+    def step_resident(self, dt, nsteps=1, first=False):
+        for k in range(nsteps):
+            self.engine.step_lfra(dt, first and k == 0, self.RAgamma)
 
 
 RKintegrators = {"rk3": _specs("rk3", 3), "ef": _specs("ef", 1), "enrk3": _specs("enrk3", 3)}

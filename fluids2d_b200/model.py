@@ -70,10 +70,15 @@ class Model:
         resident = integ.rhs is integ._device_rhs
         if resident:
             integ.upload(self.state)
+            if self.param.integrator == "LFRA":
+                integ._scratch_io(True)
         while (not self.time.finished) and (not self.stop):
             if resident:
                 self.set_dt(on_device=True)
-                integ.step_resident(self.time.dt, 1)
+                if self.param.integrator == "LFRA":
+                    integ.step_resident(self.time.dt, 1, first=self.time.ite == 0)
+                else:
+                    integ.step_resident(self.time.dt, 1)
                 self.time.pushforward()
                 if self._observation_due():
                     integ.download(self.state)
@@ -86,6 +91,8 @@ class Model:
             self.save_to_file()
         if resident:
             integ.download(self.state)
+            if self.param.integrator == "LFRA":
+                integ._scratch_io(False)
         self.progress()
         self.print_perf(_wall() - tic)
         self.finalize()
@@ -97,7 +104,7 @@ class Model:
 
     def step(self, nsteps=1):
         integ = self.integrator
-        if nsteps > 1 and integ.rhs is integ._device_rhs and self.param.dt > 0:
+        if nsteps > 1 and integ.rhs is integ._device_rhs and self.param.dt > 0 and self.param.integrator != "LFRA":
             integ.upload(self.state)
             integ.step_resident(self.time.dt, nsteps)
             integ.download(self.state)

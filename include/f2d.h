@@ -43,7 +43,7 @@ enum { F2D_MODEL_EULER = 0, F2D_MODEL_BOUSSINESQ = 1, F2D_MODEL_RSW = 2, F2D_MOD
        F2D_MODEL_EULERPSI = 4, F2D_MODEL_QG = 5, F2D_MODEL_ADVECTION = 6, F2D_MODEL_VECTORADV = 7 };
 enum { F2D_METHOD_WENO = 0, F2D_METHOD_UPWIND = 1, F2D_METHOD_CENTERED = 2, F2D_METHOD_CWENO = 3,
        F2D_METHOD_CLASSIC = 4 /* innerproduct only, operators.py:86-89 */ };
-enum { F2D_INT_RK3 = 0, F2D_INT_EF = 1, F2D_INT_ENRK3 = 2 };
+enum { F2D_INT_RK3 = 0, F2D_INT_EF = 1, F2D_INT_ENRK3 = 2, F2D_INT_LFRA = 3 };
 /* noslip.py:15-34: bit flags; F2D_NOSLIP_ALL == param.noslip is True */
 enum { F2D_NOSLIP_NONE = 0, F2D_NOSLIP_LEFT = 1, F2D_NOSLIP_RIGHT = 2, F2D_NOSLIP_BOTTOM = 4,
        F2D_NOSLIP_TOP = 8, F2D_NOSLIP_ALL = 16 };
@@ -111,6 +111,10 @@ int f2d_field_ptr(f2d_ctx *ctx, const char *field, double **d_ptr);
 /* RKIntegrator.step (integrators.py:76-79) with rk3/ef/enrk3 (:82-124):
  * nsteps fused steps at fixed dt, state stays on the device. */
 int f2d_step(f2d_ctx *ctx, double dt, int nsteps);
+/* LFRAintegrator.step (integrators.py:20-53): one leap-frog step with the
+ * Robert-Asselin filter; scratch sets ds0 = sb, ds1 = sa, ds2 = ds as in the
+ * reference's `scratch` list; first = (time.ite == 0). */
+int f2d_step_lfra(f2d_ctx *ctx, double dt, int first, double gamma);
 /* The same step in the reference's granularity, so that host callbacks
  * (model.add_forcing, equations.py:229-238) can run between the pieces:
  * ds_k = rhs(state) (equations.py:11-15 etc.) */

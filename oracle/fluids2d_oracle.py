@@ -113,7 +113,7 @@ _DEFAULTS = dict(  # param.py:13-59 (only what the hot path reads)
     model="euler", nx=40, ny=40, Lx=1.0, Ly=1.0, xperiodic=False, yperiodic=False,
     halowidth=3, noslip=None, f0=10.0, beta=0.0, g=1, H=1, dt=0.0, cfl=0.9, dtmax=9e99,
     integrator="rk3", compflux="weno", vortexforce="weno", innerproduct="weno",
-    maxorder=6, tracer=None)
+    maxorder=6, tracer=None, RAgamma=0.1)
 
 
 def make_param(**kw):
@@ -581,7 +581,7 @@ class Model:
         names, prog = SPECS[self.param.model]
         self.prognostic = prog
         self.state = _alloc(names, self.mesh.shape)
-        nst = 1 if self.param.integrator == "ef" else 3
+        nst = 1 if self.param.integrator == "ef" else 3     # LFRA: scratch = [sb, sa, ds]
         self.scratch = [_alloc(prog, self.mesh.shape) for _ in range(nst)]
         self.rhs, self.diag = rhs_and_diag(self.param, self.mesh)
         self.t, self.ite = 0.0, 0
@@ -607,6 +607,11 @@ class Model:
         dt = self.compute_dt() if dt is None else dt
         s = self.state
         ys = _leaves(s, self.prognostic)
+        if self.param.integrator == "LFRA":
+            self._step_lfra(dt, ys)
+            self.t += dt
+            self.ite += 1
+            return dt
         for k, coefs in enumerate(RK_COEFS[self.param.integrator](dt)):
             self.rhs(s, self.scratch[k])
             xs = [_leaves(self.scratch[i], self.prognostic) for i in range(k + 1)]
@@ -620,3 +625,22 @@ class Model:
         self.t += dt
         self.ite += 1
         return dt
+
+    def _step_lfra(self, dt, ys):
+        """integrators.py:39-53 with copyto (:140-151), rightpermute (:133-137)"""
+        s, gamma = self.state, self.param.RAgamma
+        sb, sa, ds = (_leaves(x, self.prognostic) for x in self.scratch)
+        self.rhs(s, self.scratch[2])
+        if self.ite == 0:
+            for f, y in enumerate(ys):
+                sb[f][:] = y
+                sa[f][:] = y
+                y[:] += 0 + dt * ds[f]
+        else:
+            for f, y in enumerate(ys):
+                sa[f][:] += 0 + (2 * dt) * ds[f]
+                y[:] += ((0 + gamma * sa[f]) + gamma * sb[f]) + (-2 * gamma) * y
+                sb[f][:] = y           # rightpermute(sa, s, sb)
+                y[:] = sa[f]
+                sa[f][:] = sb[f]
+        self.diag(s)

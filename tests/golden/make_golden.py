@@ -148,6 +148,19 @@ def case_euler_cweno():
     run_case("euler_cweno", kw, ic=lambda m: dipole_ic(m, 0.5, 0.5, 0.06, 0.06))
 
 
+def case_euler_lfra():
+    # the LFRA settings of geos_adj.py:77-81 / tracer_advection.py:91-94 on the Euler dipole
+    kw = dict(model="euler", nx=48, ny=40, integrator="LFRA", cfl=0.5, compflux="centered",
+              vortexforce="centered", innerproduct="classic")
+    run_case("euler_lfra", kw, ic=lambda m: dipole_ic(m, 0.5, 0.5, 0.06, 0.06))
+
+
+def case_rsw_lfra():
+    kw = dict(model="rsw", nx=48, ny=48, dtmax=1, f0=10.0, integrator="LFRA", cfl=0.5, compflux="centered",
+              vortexforce="centered", innerproduct="classic", RAgamma=0.05)
+    run_case("rsw_lfra", kw, ic=lambda m: rsw_ic(m))
+
+
 def rsw_ic(model, amp=0.2, r0=0.1, y0=0.5, sub_hb=False):
     """geos_adj.py:12-49 (flow='dipole'); rsw_with_topo.py:12-53 when sub_hb"""
     mesh = model.mesh
@@ -462,7 +475,7 @@ if __name__ == "__main__":
             case_euler_enrk3_upwind, case_euler_centered_ef, case_euler_cweno,
             case_rsw, case_rsw_islands, case_qgrsw_topo, case_qgrsw_islands,
             case_warm_bubble, case_lock_exchange, case_advection, case_advection_disc_upwind, case_eulerpsi,
-            case_qg, case_vectoradv, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
+            case_qg, case_vectoradv, case_euler_lfra, case_rsw_lfra, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
     for fn in todo:
         if which is None or fn.__name__ in which:
             fn()

@@ -101,10 +101,13 @@ def test_out_of_scope_models_raise():
     with pytest.raises(NotImplementedError):
         f2d.Model(p)
     p = f2d.Param()
-    p.integrator = "LFRA"
+    p.tracer = "dye"
     from fluids2d_b200._cabi import config_from_param
     with pytest.raises(NotImplementedError):
         config_from_param(p)
+    p = f2d.Param()
+    p.integrator = "LFRA"          # on the device since round 1 (f2d_step_lfra)
+    assert config_from_param(p).integrator == 3
 
 
 def test_time_is_kahan_compensated():

@@ -11,7 +11,9 @@ EULER_CASES = ["euler40", "vortex", "vortex_triangle", "disc_island", "xper_nosl
 ALL_CASES = EULER_CASES + ["rsw", "rsw_islands", "qgrsw_topo", "qgrsw_islands",
                            "warm_bubble", "lock_exchange",
                            # the remaining models on the same kernels
-                           "advection", "advection_disc_upwind", "eulerpsi", "qg", "vectoradv"]
+                           "advection", "advection_disc_upwind", "eulerpsi", "qg", "vectoradv",
+                           # leap-frog + Robert-Asselin filter
+                           "euler_lfra", "rsw_lfra"]
 
 
 class Golden:
@@ -102,7 +104,7 @@ _PARAM_DEFAULTS = dict(
     model="euler", nx=40, ny=40, Lx=1.0, Ly=1.0, xperiodic=False, yperiodic=False,
     halowidth=3, noslip=None, f0=10.0, beta=0.0, g=1, H=1, dt=0.0, cfl=0.9, dtmax=9e99,
     integrator="rk3", compflux="weno", vortexforce="weno", innerproduct="weno",
-    maxorder=6, tracer=None)
+    maxorder=6, tracer=None, RAgamma=0.1)
 
 
 def plain_param(**kw):
