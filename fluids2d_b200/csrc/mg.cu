@@ -303,36 +303,57 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
 //   pold / pnew are distinct buffers because q needs pnew at the neighbours.
 //   singular operators: z is projected on the complement of the constants, so
 //   that rounding in the V-cycle cannot feed the null space.
+//   A CTA forms pnew once per point of a (64+2) x (16+2) window in shared
+//   memory and applies the 5-point operator from there.
+constexpr int CGX = 64, CGY = 16;
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ pold,
                double *__restrict__ pnew, double *__restrict__ q, double *__restrict__ scal, int it,
                int singular, double inv_n, double *part, unsigned int *count) {
+    __shared__ double sp[CGY + 2][CGX + 2];
     double rznew = scal[S_RZNEW];
     double mz = singular ? scal[S_SUMZ] * inv_n : 0.0;
     double beta = 0.0;
     if (it > 0) { double rzold = scal[S_RZ0 + ((it - 1) & 1)]; beta = rzold != 0.0 ? rznew / rzold : 0.0; }
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY;
     double v[1] = {0.0};
-    FINE_LOOP(F) {
-        long idx;
-        if (!fine_index(F, j, i, idx)) continue;
-        uint8_t c = F.nb[idx];
-        if (!(c & NB_SELF)) continue;
-        Stencil s = fine_stencil(F, i, idx, c);
-        auto P = [&](long k) { return ((double)z[k] - mz) + beta * pold[k]; };
-        double pc = P(idx);
-        double off = 0.0;
-        if (c & NB_W) off += s.cw * P(s.iw);
-        if (c & NB_E) off += s.ce * P(s.ie);
-        if (c & NB_S) off += s.cs * P(s.is);
-        if (c & NB_N) off += s.cn * P(s.in);
-        double qv = s.diag * pc - off;
-        pnew[idx] = pc;
-        q[idx] = qv;
-        if (j >= F.jo0 && j < F.jo1) v[0] += pc * qv;
+    for (int tile = blockIdx.y * gridDim.x + blockIdx.x; tile < ntx * nty; tile += gridDim.x * gridDim.y) {
+        const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
+        __syncthreads();
+        for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
+            int a = t / (CGX + 2), b = t - a * (CGX + 2);
+            int j = j0 - 1 + a, i = i0 - 1 + b;
+            if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            double pv = 0.0;
+            long idx;
+            if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF))
+                pv = ((double)z[idx] - mz) + beta * pold[idx];
+            sp[a][b] = pv;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < CGY / 4; r++) {
+            const int a = 1 + threadIdx.y + 4 * r, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * r;
+            long idx;
+            if (i >= F.nx || j >= F.ny || !fine_index(F, j, i, idx)) continue;
+            uint8_t c = F.nb[idx];
+            if (!(c & NB_SELF)) continue;
+            double cw = (c & NB_W) ? F.cx : 0.0, ce = (c & NB_E) ? F.cx : 0.0;
+            double cs = (c & NB_S) ? F.cy : 0.0, cn = (c & NB_N) ? F.cy : 0.0;
+            double diag = F.dirichlet ? (2.0 * (F.cx + F.cy) + F.shift) : (((cw + ce) + cs) + cn + F.shift);
+            double pc = sp[a][b];
+            // closed faces lead to points that are not unknowns: their sp entry is 0
+            double qv = diag * pc - (F.cx * (sp[a][b - 1] + sp[a][b + 1]) + F.cy * (sp[a - 1][b] + sp[a + 1][b]));
+            pnew[idx] = pc;
+            q[idx] = qv;
+            if (j >= F.jo0 && j < F.jo1) v[0] += pc * qv;
+        }
     }
     grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) scal[S_RZ0 + (it & 1)] = rznew;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) scal[S_RZ0 + (it & 1)] = rznew;
 }
 
 // y = A x = -L x on the unknowns, 0 elsewhere inside the window
@@ -1522,11 +1543,11 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 F2D_TRY(vcycle_unfused(c, M, M.z, M.r, 1.0, true));
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
-                k_cg_dir_apply<double><<<nblk, 256, 0, st>>>(F, M.z, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
+                k_cg_dir_apply<double><<<nblk, dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
                                                              c->d_part, c->d_count);
             } else {
                 F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
-                k_cg_dir_apply<float><<<nblk, 256, 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
+                k_cg_dir_apply<float><<<nblk, dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
                                                             c->d_part, c->d_count);
             }
             LAUNCH_CHECK(c);
@@ -1643,7 +1664,7 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 *bytes = npts * (1.5 * 8 + 0.5);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.dir_apply") {
-                k_cg_dir_apply<float><<<nblk, 256, 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
+                k_cg_dir_apply<float><<<nblk, dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
                 *bytes = npts * (4 + 3 * 8 + 1);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.update") {

@@ -153,50 +153,61 @@ struct Window {
         }
     }
 
-    // one red-black half-sweep of colour `col` on the ring-`m` interior
+    // one red-black half-sweep of colour `col` on the ring-`m` interior.
+    // A warp owns rows a0, a0+16, ... which all have the parity of a0, so the
+    // column offset o, the bounds test and every neighbour offset are hoisted;
+    // the unrolled body is loads at constant offsets from one base pointer.
     template <bool NO_NEIGHBOURS>
     __device__ __forceinline__ void relax(int col, int m, int par0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const int a0 = m + warp;
+        const int o = col ^ ((par0 + a0) & 1), b = 2 * k + o;
+        if (b < m || b >= TW - m) return;
+        const int p0 = at(col, a0, k), q0 = at(1 - col, a0, k);
+        const int nrow = (WJ - m - a0 + TILE_WARPS - 1) / TILE_WARPS;
+        constexpr int S = TILE_WARPS * TK;
+        T *xp = X + p0;
+        const T *xq = X + q0 + o, *fp = Fv + p0;
 #pragma unroll
         for (int r = 0; r < ROWS_PER_WARP; r++) {
-            int a = m + warp + r * TILE_WARPS;
-            if (a >= WJ - m) break;
-            int rp = (par0 + a) & 1, o = col ^ rp, b = 2 * k + o;
-            if (b < m || b >= TW - m) continue;
-            int p = at(col, a, k);
-            T acc = Fv[p];
+            if (r >= nrow) break;
+            T acc = fp[r * S];
             if (!NO_NEIGHBOURS) {
-                int q = at(1 - col, a, k);
-                T xw = X[q + o - 1], xe = X[q + o], xs = X[q - TK], xn = X[q + TK];
+                const T *q = xq + r * S;
+                T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
                 if constexpr (FINE) acc += cxf * (xw + xe) + cyf * (xs + xn);
-                else acc += CX[p] * xw + CX[q + o] * xe + CY[p] * xs + CY[q + TK] * xn;
+                else acc += CX[p0 + r * S] * xw + CX[q0 + o + r * S] * xe + CY[p0 + r * S] * xs + CY[q0 + TK + r * S] * xn;
             }
-            if constexpr (FINE) X[p] = acc * tab_dinv[B[p] & 31];
-            else X[p] = acc * DI[p];
+            if constexpr (FINE) xp[r * S] = acc * tab_dinv[B[p0 + r * S] & 31];
+            else xp[r * S] = acc * DI[p0 + r * S];
         }
     }
 
     // residual, pre-multiplied by 1/normaliser of the prolongation, into Fv (ring m)
     __device__ __forceinline__ void residual(int m, int par0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const int a0 = m + warp;
+        const int rp = (par0 + a0) & 1;
+        const int nrow = (WJ - m - a0 + TILE_WARPS - 1) / TILE_WARPS;
+        constexpr int S = TILE_WARPS * TK;
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_WARP; r++) {
-            int a = m + warp + r * TILE_WARPS;
-            if (a >= WJ - m) break;
-            int rp = (par0 + a) & 1;
+        for (int col = 0; col < 2; col++) {
+            const int o = col ^ rp, b = 2 * k + o;
+            if (b < m || b >= TW - m) continue;
+            const int p0 = at(col, a0, k), q0 = at(1 - col, a0, k) + o;
 #pragma unroll
-            for (int col = 0; col < 2; col++) {
-                int o = col ^ rp, b = 2 * k + o;
-                if (b < m || b >= TW - m) continue;
-                int p = at(col, a, k), q = at(1 - col, a, k);
-                T xw = X[q + o - 1], xe = X[q + o], xs = X[q - TK], xn = X[q + TK];
+            for (int r = 0; r < ROWS_PER_WARP; r++) {
+                if (r >= nrow) break;
+                const int p = p0 + r * S;
+                const T *q = X + q0 + r * S;
+                T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
                 uint8_t bits = B[p];
                 T off, diag;
                 if constexpr (FINE) {
                     off = cxf * (xw + xe) + cyf * (xs + xn);
                     diag = tab_diag[bits & 31];
                 } else {
-                    off = CX[p] * xw + CX[q + o] * xe + CY[p] * xs + CY[q + TK] * xn;
+                    off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
                     T di = DI[p];
                     diag = di != T(0) ? T(1) / di : T(0);
                 }
@@ -331,21 +342,28 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
         }
     }
     __syncthreads();
+    // restriction R = P^T: weights (1,3,3,1) x (1,3,3,1) over the 4 x 4 fine cells
+    // around the aggregate.  In the colour-separated layout the four columns of
+    // a row are (cA,kA) (cB,kB) (cA,kC) (cB,kD) with cB = 1 - cA, and cA flips
+    // from one row to the next: four loads at fixed offsets per row.
     for (int t = threadIdx.x; t < (TJ / 2) * (TI / 2); t += TILE_THREADS) {
         int cj = t / (TI / 2), ci = t - cj * (TI / 2);
         int J = tj0 / 2 + cj, I = ti0 / 2 + ci;            // aggregate of fine rows 2J, 2J+1
         int Jc = J + L.pj_off();                           // its row in the coarse array
         if (Jc >= nyc || I >= nxc) continue;
-        int a0 = 2 * J - wj0, b0 = 2 * I - wi0;
+        const int a0 = 2 * cj + H, b0 = 2 * ci + H;        // = 2J - wj0, 2I - wi0
+        const int kA = (b0 - 1) >> 1, kB = b0 >> 1, kC = (b0 + 1) >> 1, kD = (b0 + 2) >> 1;
+        int cA = (par0 + a0 - 1 + b0 - 1) & 1;             // colour of (a0-1, b0-1)
+        constexpr int PL = WJ * TK;                        // one colour plane
+        const T *row = W.Fv + (a0 - 1) * TK;
         T acc = T(0);
 #pragma unroll
-        for (int da = -1; da <= 2; da++) {
-            T wy = (da == 0 || da == 1) ? T(3) : T(1);
-#pragma unroll
-            for (int db = -1; db <= 2; db++) {
-                T wx = (db == 0 || db == 1) ? T(3) : T(1);
-                acc += wy * wx * W.Fat(par0, a0 + da, b0 + db);
-            }
+        for (int da = 0; da < 4; da++) {
+            const T *pa = row + cA * PL, *pb = row + (1 - cA) * PL;
+            T v = (pa[kA] + pb[kD]) + T(3) * (pb[kB] + pa[kC]);
+            acc += (da == 1 || da == 2) ? T(3) * v : v;
+            row += TK;
+            cA ^= 1;
         }
         bc[(long)(Jc + 1) * pitchc + I + 1] = (TC)acc;
     }
