@@ -292,7 +292,7 @@ struct Window {
 //   TX / TF: storage types of x and f in global memory (the fine level of the
 //          CG preconditioner relaxes in fp32 on an fp64 residual)
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
 k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
           const double *__restrict__ scal, int sumr_slot, double inv_n,
           int nyc, int nxc, int pitchc, TC *__restrict__ bc) {
@@ -373,7 +373,7 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
 // UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
 // ---------------------------------------------------------------------------
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
 k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
         const double *__restrict__ scal, int sumr_slot, double inv_n,
         int nyc, int nxc, int pitchc, int periodic_c, const TC *__restrict__ xc,

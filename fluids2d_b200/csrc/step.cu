@@ -75,7 +75,7 @@ struct RkFuse {
 };
 
 template <int MV, int MODEL, int NC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_rhs_mom(Grid g, const double *__restrict__ ux, const double *__restrict__ uy,
           const double *__restrict__ omega, const double *__restrict__ ke,
           const double *__restrict__ p, const double *__restrict__ b,
