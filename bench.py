@@ -332,7 +332,7 @@ if __name__ == "__main__":
     ap.add_argument("--strong", action="store_true", help="N > 1: split the n x n grid instead of growing it with N")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent copies instead of one decomposed grid")
     ap.add_argument("--sweeps", dest="nu", type=int, default=2, help="smoothing sweeps per V-cycle leg")
-    ap.add_argument("--guess", type=int, default=3, help="first-guess extrapolation order (0 off)")
+    ap.add_argument("--guess", type=int, default=4, help="first-guess extrapolation order (0 off)")
     ap.add_argument("--rtol", type=float, default=1e-12, help="elliptic solver tolerance")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline timings")
     a = ap.parse_args()

@@ -58,7 +58,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     F2D_CUDA(cudaSetDevice(cfg->device));
     f2d_ctx *c = new f2d_ctx();
     c->cfg = *cfg;
-    c->guess_order = cfg->reserved[0] > 0 ? cfg->reserved[0] - 1 : 3;   // guess_order + 1 (0 = default)
+    c->guess_order = cfg->reserved[0] > 0 ? cfg->reserved[0] - 1 : 4;   // guess_order + 1 (0 = default)
     c->nh = cfg->nh;
     c->n1 = cfg->nx + 2 * cfg->nh;
     c->n2 = cfg->ny + 2 * cfg->nh;

@@ -125,7 +125,7 @@ struct Multigrid {
 
 namespace f2d {
 struct GuessHistory {            // last solutions of one RK stage's elliptic solve
-    double *g[3] = {nullptr, nullptr, nullptr};
+    double *g[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int valid = 0;
 };
 }  // namespace f2d
@@ -153,7 +153,7 @@ struct f2d_ctx {
     f2d::Multigrid mg[3];
     f2d::Dist dist;
     f2d::GuessHistory guess[3];
-    int guess_order = 3;            // 0 off, 1 previous step, 2 linear, 3 quadratic extrapolation
+    int guess_order = 4;            // 0 off, 1 previous step, 2 linear, 3 quadratic, 4 cubic ... 6
     int stage_hint = -1;
     // reductions
     double *d_scal = nullptr;       // device scalars

@@ -671,25 +671,38 @@ static int launch_divflux(f2d_ctx *c, const double *q, double *dq, bool direct_U
 // stage k changes slowly from one time step to the next, while it differs by
 // O(1) between stages (the incremental RK form scales each stage's pressure by
 // other coefficients) -- so the guess is extrapolated from the SAME stage of the
-// previous steps: x0 = 2 g1 - g2 (or g1, or what x holds, as history allows).
+// previous steps by polynomial extrapolation (order = param.solver_guess, as far
+// as the history allows; 0 keeps what x holds).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_guess(long n, double *__restrict__ x, const double *__restrict__ g1, const double *__restrict__ g2,
-        const double *__restrict__ g3, int order) {
+struct GuessArgs { const double *g[6]; double w[6]; int n; };
+__global__ void __launch_bounds__(256) k_guess(long n, double *__restrict__ x, GuessArgs A) {
     long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    if (order == 1) x[k] = g1[k];
-    else if (order == 2) x[k] = 2.0 * g1[k] - g2[k];
-    else x[k] = 3.0 * (g1[k] - g2[k]) + g3[k];
+    double v = A.w[0] * A.g[0][k];
+#pragma unroll
+    for (int m = 1; m < 6; m++)
+        if (m < A.n) v += A.w[m] * A.g[m][k];
+    x[k] = v;
 }
 
+// polynomial extrapolation through the last `order` solutions of this stage
+// (equal steps): x0 = sum_k (-1)^(k+1) C(order, k) g_k
 static int guess_before(f2d_ctx *c, int stage, double *x) {
     if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
     GuessHistory &G = c->guess[stage];
-    int order = std::min(G.valid, c->guess_order);
+    int order = std::min(G.valid, std::min(c->guess_order, 6));
     if (order <= 0) return F2D_OK;
+    GuessArgs A;
+    A.n = order;
+    double binom = 1.0;
+    for (int k = 1; k <= order; k++) {
+        binom = binom * (order - k + 1) / k;
+        A.g[k - 1] = G.g[k - 1];
+        A.w[k - 1] = (k & 1) ? binom : -binom;
+    }
+    for (int k = order; k < 6; k++) { A.g[k] = nullptr; A.w[k] = 0.0; }
     long n = (long)c->n;
-    k_guess<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, x, G.g[0], G.g[1], G.g[2], order);
+    k_guess<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, x, A);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -697,17 +710,18 @@ static int guess_before(f2d_ctx *c, int stage, double *x) {
 static int guess_after(f2d_ctx *c, int stage, const double *x) {
     if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
     GuessHistory &G = c->guess[stage];
-    for (int k = 0; k < std::min(c->guess_order, 3); k++)
+    const int depth = std::min(c->guess_order, 6);
+    for (int k = 0; k < depth; k++)
         if (!G.g[k]) {
             F2D_CUDA(cudaMalloc(&G.g[k], c->n * sizeof(double)));
             F2D_CUDA(cudaMemsetAsync(G.g[k], 0, c->n * sizeof(double), c->stream));
         }
     // rotate: g3 <- g2 <- g1 <- x
-    double *last = G.g[std::min(c->guess_order, 3) - 1];
-    for (int k = std::min(c->guess_order, 3) - 1; k > 0; k--) G.g[k] = G.g[k - 1];
+    double *last = G.g[depth - 1];
+    for (int k = depth - 1; k > 0; k--) G.g[k] = G.g[k - 1];
     G.g[0] = last;
     F2D_CUDA(cudaMemcpyAsync(G.g[0], x, c->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    G.valid = std::min(G.valid + 1, 3);
+    G.valid = std::min(G.valid + 1, 6);
     return F2D_OK;
 }
 

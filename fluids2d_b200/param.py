@@ -59,8 +59,8 @@ class Param:
         self.solver_rtol = 1e-12     # ||b - A x|| <= rtol ||b||
         self.solver_maxit = 100
         self.solver_nu = 2           # red-black sweeps before and after each coarse correction
-        self.solver_guess = 3        # first guess from the same RK stage of earlier steps: 0 off,
-                                     # 1 previous, 2 linear, 3 quadratic extrapolation
+        self.solver_guess = 4        # first guess from the same RK stage of earlier steps: 0 off,
+                                     # 1 previous, 2 linear, 3 quadratic, 4 cubic extrapolation (max 6)
         self.__parameters__ = _public_names(self)
         self.help()
 

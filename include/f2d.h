@@ -72,7 +72,8 @@ typedef struct {
                              * [4]: non-zero when param.beta != 0 (qg: unsupported);
                              * [0]: 1 + order of the first-guess extrapolation across
                              * time steps for the solves inside f2d_step (0 = default
-                             * = quadratic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic) */
+                             * = cubic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic,
+                             * 5 = cubic, up to 7) */
 } f2d_config;
 
 int f2d_version(void);
