@@ -133,9 +133,8 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
             f"model '{param.model}' is not on the device path ({', '.join(MODELS)})")
     if param.integrator not in INTEGRATORS:
         raise NotImplementedError(f"integrator '{param.integrator}' is not on the device path")
-    if getattr(param, "tracer", None) not in (None, "None"):
-        raise NotImplementedError("tracer equations are not on the device path yet")
     cfg = Config()
+    cfg.reserved[5] = int(getattr(param, "tracer", None) not in (None, "None"))
     cfg.model = MODELS[param.model]
     cfg.nx, cfg.ny, cfg.nh = param.nx, param.ny, param.halowidth
     if slab is not None and slab.nranks > 1:
@@ -175,6 +174,9 @@ class Engine:
         self.shape = (self.cfg.ny + 2 * param.halowidth, param.nx + 2 * param.halowidth)
         self.size = self.shape[0] * self.shape[1]
         self._h = C.c_void_p()
+        # the device calls the extra scalar "tracer" whatever param.tracer names it
+        t = getattr(param, "tracer", None)
+        self._tracer = t if t not in (None, "None") else None
         self._chk(self.lib.f2d_create(C.byref(self.cfg), C.byref(self._h)))
         self._dev_allocs = []
         if self.slab is not None:
@@ -184,6 +186,15 @@ class Engine:
             _preload_nccl()
             assert (rank, world) == (self.slab.rank, self.slab.nranks)
             self._chk(self.lib.f2d_dist_init(self._h, rank, world, uid))
+
+    def _n(self, name):
+        """host leaf name -> device field name (bytes)"""
+        if self._tracer is not None:
+            if name == self._tracer:
+                name = "tracer"
+            elif name.startswith("ds") and name.endswith("." + self._tracer) and name[2:3].isdigit():
+                name = name[:name.index(".") + 1] + "tracer"
+        return name.encode()
 
     # -- errors -------------------------------------------------------------
     def _chk(self, status):
@@ -231,33 +242,33 @@ class Engine:
     def upload(self, name, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert a.shape == self.shape, (name, a.shape, self.shape)
-        self._chk(self.lib.f2d_upload(self._h, name.encode(), _ptr(a)))
+        self._chk(self.lib.f2d_upload(self._h, self._n(name), _ptr(a)))
         if self.slab is not None and not name.startswith("ds"):
-            self._chk(self.lib.f2d_dist_exchange(self._h, name.encode()))
+            self._chk(self.lib.f2d_dist_exchange(self._h, self._n(name)))
         self.sync()     # `a` may be a temporary
 
     def upload_async(self, name, a):
         assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == self.shape
-        self._chk(self.lib.f2d_upload(self._h, name.encode(), _ptr(a)))
+        self._chk(self.lib.f2d_upload(self._h, self._n(name), _ptr(a)))
         if self.slab is not None and not name.startswith("ds"):
             # host ghost rows may be stale: take them from their owners
-            self._chk(self.lib.f2d_dist_exchange(self._h, name.encode()))
+            self._chk(self.lib.f2d_dist_exchange(self._h, self._n(name)))
 
     def download(self, name, out=None):
         if out is None:
             out = np.empty(self.shape, dtype=np.float64)
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == self.shape
-        self._chk(self.lib.f2d_download(self._h, name.encode(), _ptr(out)))
+        self._chk(self.lib.f2d_download(self._h, self._n(name), _ptr(out)))
         self.sync()
         return out
 
     def download_async(self, name, out):
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == self.shape
-        self._chk(self.lib.f2d_download(self._h, name.encode(), _ptr(out)))
+        self._chk(self.lib.f2d_download(self._h, self._n(name), _ptr(out)))
 
     def field_ptr(self, name):
         p = C.c_void_p()
-        self._chk(self.lib.f2d_field_ptr(self._h, name.encode(), C.byref(p)))
+        self._chk(self.lib.f2d_field_ptr(self._h, self._n(name), C.byref(p)))
         return p.value
 
     def sync(self):

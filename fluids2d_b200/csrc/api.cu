@@ -118,6 +118,15 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
         c->prognostic = {"v.x", "v.y"};
         break;
     }
+    c->tracer = cfg->reserved[5] != 0;
+    if (c->tracer) {                    // states.py:23-34: one more prognostic scalar
+        names.push_back("tracer");
+        c->prognostic.push_back("tracer");
+        if (std::find(names.begin(), names.end(), "flx.x") == names.end()) {
+            names.push_back("flx.x");
+            names.push_back("flx.y");
+        }
+    }
     c->nstages = cfg->integrator == F2D_INT_EF ? 1 : 3;
     for (auto &nm : names) F2D_TRY(alloc_field(c, nm));
     for (int k = 0; k < c->nstages; k++)

@@ -153,6 +153,7 @@ struct f2d_ctx {
     f2d::Multigrid mg[3];
     f2d::Dist dist;
     f2d::GuessHistory guess[3];
+    bool tracer = false;            // param.tracer: extra advected scalar "tracer" (equations.py:217-226)
     int guess_order = 4;            // 0 off, 1 previous step, 2 linear, 3 quadratic, 4 cubic ... 6
     int stage_hint = -1;
     // reductions

@@ -186,6 +186,24 @@ k_divflux(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
     dq[k_out] = d * (double)msk[k];
 }
 
+// The tracer tendency (equations.py:217-222) is the same `div` WITHOUT the fill
+// that follows every model-owned scalar: halo columns hold what `div` itself
+// leaves there.  operators.py:105 does not assign the last column, so there the
+// y-difference accumulates onto the previous content of dq (visible only when
+// the halo mask is 1, i.e. xperiodic).
+__global__ void __launch_bounds__(256)
+k_divflux_nofill(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
+                 const int8_t *__restrict__ msk, double *__restrict__ dq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.n1 || j >= g.n2) return;
+    long k = (long)j * g.n1 + i;
+    int m = msk[k];
+    double d = (i <= g.n1 - 2) ? -(fx[k + 1] - fx[k]) : (m ? dq[k] : 0.0);
+    if (j <= g.n2 - 2) d -= fy[k + g.n1] - fy[k];
+    dq[k] = d * (double)m;
+}
+
 // ---------------------------------------------------------------------------
 // addto_list (integrators.py:154-174): y += ((0 + c0 x0) + c1 x1) + c2 x2
 // ---------------------------------------------------------------------------
@@ -645,7 +663,7 @@ static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy, RkFuse rk = RkFu
 
 // direct_U: the model's transport velocity IS the contravariant state.U
 // (eulerpsi, qg, advection), not sharp(u)
-static int launch_divflux(f2d_ctx *c, const double *q, double *dq, bool direct_U = false) {
+static int launch_divflux(f2d_ctx *c, const double *q, double *dq, bool direct_U = false, bool fill = true) {
     Grid g = grid_of(c);
     if (direct_U) g.idx2 = g.idy2 = 1.0;
     const double *vx = direct_U ? c->f("U.x") : c->f("u.x"), *vy = direct_U ? c->f("U.y") : c->f("u.y");
@@ -660,9 +678,19 @@ static int launch_divflux(f2d_ctx *c, const double *q, double *dq, bool direct_U
     }
 #undef FLX_ARGS
     LAUNCH_CHECK(c);
-    k_divflux<<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dq);
+    if (fill) k_divflux<<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dq);
+    else k_divflux_nofill<<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dq);
     LAUNCH_CHECK(c);
     return F2D_OK;
+}
+
+// addtracerequation (equations.py:217-226): after the model's own tendency,
+// ds.tracer = -div(flux(tracer, s.U)), not filled
+static int tracer_rhs(f2d_ctx *c, int k) {
+    const int m = c->cfg.model;
+    const bool direct = m == F2D_MODEL_EULERPSI || m == F2D_MODEL_QG || m == F2D_MODEL_ADVECTION ||
+                        m == F2D_MODEL_VECTORADV;
+    return launch_divflux(c, c->f("tracer"), c->f("ds" + std::to_string(k) + ".tracer"), direct, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -727,9 +755,16 @@ static int guess_after(f2d_ctx *c, int stage, const double *x) {
 
 static std::string dsname(int k, const char *leaf) { return "ds" + std::to_string(k) + "." + leaf; }
 
+static int model_rhs_core(f2d_ctx *c, int k);
+
 int model_rhs(f2d_ctx *c, int k) {
     if (!c->mesh_ready) { set_error("f2d_rhs before f2d_set_mask"); return F2D_ERR_STATE; }
     if (k < 0 || k >= c->nstages) { set_error("stage %d out of range", k); return F2D_ERR_ARG; }
+    F2D_TRY(model_rhs_core(c, k));
+    return c->tracer ? tracer_rhs(c, k) : F2D_OK;
+}
+
+static int model_rhs_core(f2d_ctx *c, int k) {
     Grid g = grid_of(c);
     switch (c->cfg.model) {     // the scalar-transport models have no momentum tendency
     case F2D_MODEL_EULERPSI: return launch_divflux(c, c->f("omega"), c->f(dsname(k, "omega")), true);
@@ -986,20 +1021,25 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
         void *a[2] = {c->tmp[0], c->tmp[1]};
         F2D_TRY(dist_exchange(c, 2, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
     }
-    if (bouss) {
-        // buoyancy: tendency from the old b (the momentum kernel above has read it), then update
-        F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
+    // advected scalars: tendency from the old u (u.x/u.y are still the old velocity,
+    // the momentum kernel wrote u* aside), then their RK update
+    auto update_scalar = [&](const char *leaf) -> int {
         long n = (long)c->n;
         unsigned grd = (unsigned)((n + 255) / 256);
-        double *y = c->f("b");
-        const double *x0 = c->f(dsname(0, "b")), *x1 = nc > 1 ? c->f(dsname(1, "b")) : nullptr,
-                     *x2 = nc > 2 ? c->f(dsname(2, "b")) : nullptr;
+        double *y = c->f(leaf);
+        const double *x0 = c->f(dsname(0, leaf)), *x1 = nc > 1 ? c->f(dsname(1, leaf)) : nullptr,
+                     *x2 = nc > 2 ? c->f(dsname(2, leaf)) : nullptr;
         if (nc == 1) k_addto<1><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], 0, 0);
         else if (nc == 2) k_addto<2><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], 0);
         else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], co[2]);
         LAUNCH_CHECK(c);
         if (c->dist.on) F2D_TRY(dist_exchange1(c, y, (size_t)c->n1 * sizeof(double), c->n2, 0));
-    }
+        return F2D_OK;
+    };
+    if (bouss) F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
+    if (c->tracer) F2D_TRY(tracer_rhs(c, s));
+    if (bouss) F2D_TRY(update_scalar("b"));
+    if (c->tracer) F2D_TRY(update_scalar("tracer"));
     return model_diag_impl(c, true);
 }
 

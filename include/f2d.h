@@ -70,6 +70,9 @@ typedef struct {
     int32_t nu1, nu2;       /* red-black sweeps before / after; 0 -> 2       */
     int32_t reserved[8];    /* [1], [2], [3]: slab decomposition, see f2d_dist_init;
                              * [4]: non-zero when param.beta != 0 (qg: unsupported);
+                             * [5]: non-zero adds the passive scalar of param.tracer
+                             *      (states.py:23-34, equations.py:217-226) as the device
+                             *      field "tracer" (tendencies "ds<k>.tracer");
                              * [0]: 1 + order of the first-guess extrapolation across
                              * time steps for the solves inside f2d_step (0 = default
                              * = cubic; 1 = off, 2 = previous step, 3 = linear, 4 = quadratic,

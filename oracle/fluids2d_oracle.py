@@ -550,7 +550,25 @@ def rhs_and_diag(param, mesh):
             fill(s.omega); fill(s.q)
     else:
         raise NotImplementedError(model)
+
+    if param.tracer and param.tracer != "None":          # equations.py:206-208, 217-226
+        model_rhs, name = rhs, param.tracer
+
+        def rhs(s, ds):
+            model_rhs(s, ds)
+            divflux(param, mesh, s.flx, getattr(s, name), s.U, getattr(ds, name))
     return rhs, diag
+
+
+def specs_of(param):                                     # states.py:22-34
+    names, prog = SPECS[param.model]
+    if param.tracer and param.tracer != "None":
+        newprog = prog + (param.tracer,)
+        names = newprog + names[len(prog):]
+        if "flx" not in names:
+            names = names + ("flx",)
+        prog = newprog
+    return names, prog
 
 
 def _leaves(ns, names):
@@ -578,7 +596,7 @@ class Model:
         self._alloc_state()
 
     def _alloc_state(self):
-        names, prog = SPECS[self.param.model]
+        names, prog = specs_of(self.param)
         self.prognostic = prog
         self.state = _alloc(names, self.mesh.shape)
         nst = 1 if self.param.integrator == "ef" else 3     # LFRA: scratch = [sb, sa, ds]

@@ -246,6 +246,53 @@ def case_lock_exchange():
     run_case("lock_exchange", kw, ic=lock_ic)
 
 
+# ---- param.tracer: one more advected scalar (states.py:23-34, equations.py:217-226) ----
+def checker_tracer(model, name):
+    # tracer_advection.py:44-48
+    x, y = model.mesh.xy("c")
+    q = getattr(model.state, name)
+    q[:, :] = (np.round(x * 8) % 2 + np.round(y * 8) % 2) / 2
+    q *= model.mesh.msk
+
+
+def case_euler_tracer():
+    kw = dict(model="euler", nx=64, ny=64, noslip=True, tracer="dye")
+
+    def mask(model):
+        x, y = model.mesh.xy()
+        msk = model.mesh.msk
+        msk[(x - 0.5) ** 2 + (y - 0.5) ** 2 > 0.48 ** 2] = 0
+        msk[(x - 0.6) ** 2 + (y - 0.35) ** 2 < 0.07 ** 2] = 0
+
+    def ic(model):
+        checker_tracer(model, "dye")
+        dipole_ic(model, 0.5, 0.6, 0.06, 0.06)
+
+    run_case("euler_tracer", kw, mask_fn=mask, ic=ic)
+
+
+def case_lock_exchange_tracer():
+    # x-periodic: the tracer tendency is NOT filled by the reference, its halo columns
+    # evolve on their own (equations.py:217-222 sits outside the model's fill)
+    kw = dict(model="boussinesq", nx=100, Lx=5.0, ny=20, cfl=0.9, dtmax=1.0, xperiodic=True, tracer="c")
+
+    def ic(model):
+        checker_tracer(model, "c")
+        lock_ic(model)
+
+    run_case("lock_exchange_tracer", kw, ic=ic)
+
+
+def case_rsw_tracer():
+    kw = dict(model="rsw", nx=64, ny=56, dtmax=1, f0=10.0, tracer="age")
+
+    def ic(model):
+        checker_tracer(model, "age")
+        rsw_ic(model)
+
+    run_case("rsw_tracer", kw, mask_fn=island_mask, ic=ic)
+
+
 # ---- the scalar-transport / stream-function models ----------
 def case_advection():
     # tests/test_models.py:17-26 set-up (body rotation + checkerboard tracer)
@@ -475,7 +522,8 @@ if __name__ == "__main__":
             case_euler_enrk3_upwind, case_euler_centered_ef, case_euler_cweno,
             case_rsw, case_rsw_islands, case_qgrsw_topo, case_qgrsw_islands,
             case_warm_bubble, case_lock_exchange, case_advection, case_advection_disc_upwind, case_eulerpsi,
-            case_qg, case_vectoradv, case_euler_lfra, case_rsw_lfra, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
+            case_qg, case_vectoradv, case_euler_lfra, case_rsw_lfra,
+            case_euler_tracer, case_lock_exchange_tracer, case_rsw_tracer, run_to_tend, ops_vectors, solve_vectors, mesh_vectors]
     for fn in todo:
         if which is None or fn.__name__ in which:
             fn()

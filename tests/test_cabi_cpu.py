@@ -101,10 +101,10 @@ def test_out_of_scope_models_raise():
     with pytest.raises(NotImplementedError):
         f2d.Model(p)
     p = f2d.Param()
-    p.tracer = "dye"
+    p.tracer = "dye"               # on the device: reserved[5] (equations.py:217-226)
     from fluids2d_b200._cabi import config_from_param
-    with pytest.raises(NotImplementedError):
-        config_from_param(p)
+    assert config_from_param(p).reserved[5] == 1
+    assert config_from_param(f2d.Param()).reserved[5] == 0
     p = f2d.Param()
     p.integrator = "LFRA"          # on the device since round 1 (f2d_step_lfra)
     assert config_from_param(p).integrator == 3

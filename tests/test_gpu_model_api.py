@@ -180,3 +180,34 @@ def test_install_as_fluids2d_alias(f2d):
     import sys
     for k in [k for k in sys.modules if k == "fluids2d" or k.startswith("fluids2d.")]:
         del sys.modules[k]
+
+
+@pytest.mark.parametrize("case", ["euler_tracer", "rsw_tracer"])
+def test_param_tracer_through_model(f2d, case):
+    """param.tracer = "<name>" adds a prognostic scalar of that name to the state and
+    the integrator scratch (states.py:23-34) advected by s.U (equations.py:217-226);
+    stepped both per step through host buffers and resident on the device."""
+    g = Golden(case)
+    name = g.param["tracer"]
+    for resident in (False, True):
+        p = f2d.Param()
+        for k, v in g.param.items():
+            setattr(p, k, v)
+        model = f2d.Model(p)
+        model.mesh.msk[:] = g.msk
+        model.mesh.finalize()
+        assert model.state._fields[:len(model.integrator.scratch[0]._fields)] == model.integrator.scratch[0]._fields
+        assert name in model.integrator.scratch[0]._fields
+        set_state(model.state, g.fields("init"))
+        if resident:
+            model.integrator.upload(model.state)
+            for dt in g.dts:
+                model.integrator.step_resident(dt, 1)
+            model.integrator.download(model.state)
+        else:
+            for dt in g.dts:
+                model.set_dt()
+                assert abs(model.time.dt - dt) <= 1e-12 * dt
+                model.step(1)
+        ref = g.fields("final")[name]
+        assert rel_l2(getattr(model.state, name), ref, model.mesh.msk) <= 1e-10, (case, resident)

@@ -13,7 +13,9 @@ ALL_CASES = EULER_CASES + ["rsw", "rsw_islands", "qgrsw_topo", "qgrsw_islands",
                            # the remaining models on the same kernels
                            "advection", "advection_disc_upwind", "eulerpsi", "qg", "vectoradv",
                            # leap-frog + Robert-Asselin filter
-                           "euler_lfra", "rsw_lfra"]
+                           "euler_lfra", "rsw_lfra",
+                           # param.tracer: the extra advected scalar (equations.py:217-226)
+                           "euler_tracer", "lock_exchange_tracer", "rsw_tracer"]
 
 
 class Golden:
