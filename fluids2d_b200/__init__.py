@@ -19,5 +19,5 @@ def install_as_fluids2d():
     import sys
     sys.modules["fluids2d"] = sys.modules[__name__]
     for sub in ("param", "model", "tools", "meshes", "states", "integrators", "equations",
-                "operators", "weno", "elliptic", "timeline"):
+                "operators", "weno", "elliptic", "timeline", "io", "diagnostics"):
         sys.modules[f"fluids2d.{sub}"] = importlib.import_module(f"{__name__}.{sub}")

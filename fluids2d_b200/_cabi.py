@@ -61,6 +61,9 @@ SIGNATURES = {
     "f2d_upload": (_I, [_P, C.c_char_p, _P]),
     "f2d_download": (_I, [_P, C.c_char_p, _P]),
     "f2d_field_ptr": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
+    "f2d_download_f32": (_I, [_P, C.c_char_p, _P]),
+    "f2d_io_sync": (_I, [_P]),
+    "f2d_bulk_sums": (_I, [_P, _I, C.POINTER(_D)]),
     "f2d_step": (_I, [_P, _D, _I]),
     "f2d_step_lfra": (_I, [_P, _D, _I, _D]),
     "f2d_rhs": (_I, [_P, _I]),
@@ -270,6 +273,23 @@ class Engine:
         p = C.c_void_p()
         self._chk(self.lib.f2d_field_ptr(self._h, self._n(name), C.byref(p)))
         return p.value
+
+    def download_f32_async(self, name, out):
+        """float32 copy of a device field into `out` (pinned float32) on the copy
+        stream; io_sync() before reading it"""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.size
+        self._chk(self.lib.f2d_download_f32(self._h, self._n(name), _ptr(out)))
+
+    def io_sync(self):
+        self._chk(self.lib.f2d_io_sync(self._h))
+
+    def bulk_sums(self):
+        """[sum ke, sum omega^2, sum omega, sum U.y*xv, sum U.x*yu, sum msk] of the
+        device state (diagnostics.py:39-62)"""
+        out = (_D * 6)()
+        row0 = self.slab.row0 if self.slab is not None else 0
+        self._chk(self.lib.f2d_bulk_sums(self._h, int(row0), out))
+        return np.array(out[:])
 
     def sync(self):
         self._chk(self.lib.f2d_sync(self._h))

@@ -155,6 +155,13 @@ int f2d_destroy(f2d_ctx *c) {
     for (auto &G : c->guess) for (double *g : G.g) cudaFree(g);
     for (auto &kv : c->mesh) cudaFree(kv.second);
     for (auto &kv : c->fields) cudaFree(kv.second);
+    if (c->io_stream) cudaStreamSynchronize(c->io_stream);
+    for (auto &kv : c->io_stage) {
+        cudaFree(kv.second.d);
+        cudaEventDestroy(kv.second.filled);
+        cudaEventDestroy(kv.second.drained);
+    }
+    if (c->io_stream) cudaStreamDestroy(c->io_stream);
     cudaFree(c->hb);
     for (double *t : c->tmp) cudaFree(t);
     cudaFree(c->d_scal);
@@ -259,6 +266,24 @@ int f2d_download(f2d_ctx *c, const char *field, double *h_dst) {
     NEED(h_dst, "null destination");
     F2D_CUDA(cudaMemcpyAsync(h_dst, p, c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return F2D_OK;
+}
+
+int f2d_download_f32(f2d_ctx *c, const char *field, float *h_dst) {
+    double *p;
+    F2D_TRY(find_field(c, field, &p));
+    NEED(h_dst, "null destination");
+    return download_f32(c, p, field, h_dst);
+}
+
+int f2d_io_sync(f2d_ctx *c) {
+    NEED(c, "null ctx");
+    if (c->io_stream) F2D_CUDA(cudaStreamSynchronize(c->io_stream));
+    return F2D_OK;
+}
+
+int f2d_bulk_sums(f2d_ctx *c, int row0, double *out6) {
+    NEED(c && out6, "null argument");
+    return bulk_sums(c, row0, out6);
 }
 
 int f2d_field_ptr(f2d_ctx *c, const char *field, double **d_ptr) {

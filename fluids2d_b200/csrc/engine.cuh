@@ -153,6 +153,10 @@ struct f2d_ctx {
     f2d::Multigrid mg[3];
     f2d::Dist dist;
     f2d::GuessHistory guess[3];
+    // history output (io.py:12-32): float32 staging + a copy stream of its own
+    struct IoStage { float *d = nullptr; cudaEvent_t filled = nullptr, drained = nullptr; };
+    std::map<std::string, IoStage> io_stage;
+    cudaStream_t io_stream = nullptr;
     bool tracer = false;            // param.tracer: extra advected scalar "tracer" (equations.py:217-226)
     int guess_order = 4;            // 0 off, 1 previous step, 2 linear, 3 quadratic, 4 cubic ... 6
     int stage_hint = -1;
@@ -182,6 +186,8 @@ int model_diag(f2d_ctx *c);
 int model_step(f2d_ctx *c, double dt, int nsteps);
 int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma);
 int max_abs_U(f2d_ctx *c, double *out);
+int bulk_sums(f2d_ctx *c, int row0, double *out);
+int download_f32(f2d_ctx *c, const double *src, const std::string &key, float *h_dst);
 // mg.cu
 int mg_build(f2d_ctx *c, int which);
 void mg_free(f2d_ctx *c, int which);

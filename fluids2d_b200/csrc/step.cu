@@ -1125,6 +1125,84 @@ int max_abs_U(f2d_ctx *c, double *out) {
 
 
 // ---------------------------------------------------------------------------
+// Bulk diagnostics (diagnostics.py:39-62): the six whole-array sums behind
+// ke / enstrophy / vorticity / angular momentum, in ONE pass over the state:
+//   out = [ sum ke, sum omega^2, sum omega, sum U.y*xv, sum U.x*yu, sum msk ]
+// xv = (i - nh + 0.5) dx, yu = (j + row0 - nh + 0.5) dy  (meshes.py:56-65).
+// The reference sums the whole haloed array; slabs sum the rows they own.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bulk(int n1, int j0, int j1, int nh, int row0, double dx, double dy,
+       const double *__restrict__ ke, const double *__restrict__ om, const double *__restrict__ Ux,
+       const double *__restrict__ Uy, const int8_t *__restrict__ msk, double *part,
+       unsigned int *count, double *out) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    long n = (long)(j1 - j0) * n1;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+        int j = j0 + (int)(t / n1), i = (int)(t % n1);
+        long k = (long)j * n1 + i;
+        double w = om[k];
+        v[0] += ke[k];
+        v[1] += w * w;
+        v[2] += w;
+        v[3] += Uy[k] * (((double)(i - nh) + 0.5) * dx);
+        v[4] += Ux[k] * (((double)(j + row0 - nh) + 0.5) * dy);
+        v[5] += (double)msk[k];
+    }
+    grid_reduce<OpSum, 6>(v, part, count, out);
+}
+
+int bulk_sums(f2d_ctx *c, int row0, double *out) {
+    if (!c->mesh_ready) { set_error("f2d_bulk_sums before f2d_set_mask"); return F2D_ERR_STATE; }
+    if (!(c->has("ke") && c->has("omega") && c->has("U.x"))) {
+        set_error("bulk diagnostics need ke, omega and U (euler, boussinesq, rsw, qgrsw)");
+        return F2D_ERR_UNSUPPORTED;
+    }
+    int gs = c->cfg.reserved[1], gn = c->cfg.reserved[2];
+    int j0 = gs > 0 ? c->nh + gs : 0, j1 = gn > 0 ? c->n2 - c->nh - gn : c->n2;
+    int nb = c->nsm * 4;
+    k_bulk<<<nb, 256, 0, c->stream>>>(c->n1, j0, j1, c->nh, row0, c->dx, c->dy, c->f("ke"), c->f("omega"),
+                                      c->f("U.x"), c->f("U.y"), c->m("msk"), c->d_part, c->d_count, c->d_scal + 16);
+    LAUNCH_CHECK(c);
+    F2D_TRY(dist_allreduce(c, c->d_scal + 16, 6, false));
+    F2D_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    F2D_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 6; k++) out[k] = c->h_scal[16 + k];
+    return F2D_OK;
+}
+
+// ---------------------------------------------------------------------------
+// History output (io.py:12-32 stores float32): convert on the device into a
+// per-field float32 staging buffer (step stream), copy it out on a separate
+// stream so the step loop keeps running; f2d_io_sync waits for the copies.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_to_f32(long n, const double *__restrict__ a, float *__restrict__ b) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) b[k] = (float)a[k];
+}
+
+int download_f32(f2d_ctx *c, const double *src, const std::string &key, float *h_dst) {
+    if (!c->io_stream) F2D_CUDA(cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking));
+    f2d_ctx::IoStage &st = c->io_stage[key];
+    if (!st.d) {
+        F2D_CUDA(cudaMalloc(&st.d, c->n * sizeof(float)));
+        F2D_CUDA(cudaEventCreateWithFlags(&st.filled, cudaEventDisableTiming));
+        F2D_CUDA(cudaEventCreateWithFlags(&st.drained, cudaEventDisableTiming));
+    } else {
+        F2D_CUDA(cudaStreamWaitEvent(c->stream, st.drained, 0));   // previous copy of this buffer
+    }
+    long n = (long)c->n;
+    k_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, src, st.d);
+    LAUNCH_CHECK(c);
+    F2D_CUDA(cudaEventRecord(st.filled, c->stream));
+    F2D_CUDA(cudaStreamWaitEvent(c->io_stream, st.filled, 0));
+    F2D_CUDA(cudaMemcpyAsync(h_dst, st.d, c->n * sizeof(float), cudaMemcpyDeviceToHost, c->io_stream));
+    F2D_CUDA(cudaEventRecord(st.drained, c->io_stream));
+    return F2D_OK;
+}
+
+// ---------------------------------------------------------------------------
 // bench.py hook: time one kernel alone, `reps` launches between two events on
 // the context's stream.  *bytes = algorithmic bytes of ONE launch (every
 // distinct array read once / written once, fp64 = 8 B, masks = 1 B).

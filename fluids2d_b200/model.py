@@ -6,24 +6,11 @@ from time import time as _wall
 from . import weno as _weno
 from .equations import addforcingterm
 from .integrators import get_integrator
+from .io import IO
 from .meshes import Mesh
 from .param import DEVICE_MODELS
 from .states import State
 from .timeline import Time
-
-
-class _NoIO:
-    """history output stays on the host application (SURVEY: io.py is out of
-    scope); nhis > 0 needs a writer object with .write(state, time)"""
-
-    def __init__(self, param):
-        if param.nhis > 0:
-            raise NotImplementedError(
-                "NetCDF history stays on the host: set model.io to an object with "
-                "write(state, time) (e.g. the reference's fluids2d.io.IO) or use nhis = 0")
-
-    def write(self, state, time):
-        pass
 
 
 class Model:
@@ -38,7 +25,8 @@ class Model:
         self.state = State(param, self.mesh.shape)
         self.set_integrator()
         self.time = Time(param)
-        self.io = _NoIO(param)
+        self.io = IO(param, self.mesh, self.state, self.time)
+        self._resident = False        # True while run() keeps the state on the device
         self.callbacks = []
         self.diags = []
         self.stop = False
@@ -48,8 +36,12 @@ class Model:
 
     # ------------------------------------------------------------------ run ---
     def _observation_due(self):
+        """does anything at this observation point (model.py:48-51) read the HOST
+        state?  Device-side observers (diagnostics.Bulk, io.IO) do not."""
         t = self.time
-        return bool(self.diags) or t.update_anim or t.save_to_file or t.finished
+        host_diags = any(not getattr(d, "on_device", False) for d in self.diags)
+        host_io = t.save_to_file and not getattr(self.io, "on_device", False)
+        return host_diags or t.update_anim or host_io or t.finished
 
     def run(self):
         if self.param.animation:
@@ -65,13 +57,16 @@ class Model:
         except ValueError:
             pass                      # not in the main thread
         tic = _wall()
-        self.save_to_file()
         integ = self.integrator
         resident = integ.rhs is integ._device_rhs
         if resident:
             integ.upload(self.state)
             if self.param.integrator == "LFRA":
                 integ._scratch_io(True)
+        self._resident = resident
+        if hasattr(self.io, "resident"):
+            self.io.resident = resident
+        self.save_to_file()
         while (not self.time.finished) and (not self.stop):
             if resident:
                 self.set_dt(on_device=True)
@@ -93,6 +88,11 @@ class Model:
             integ.download(self.state)
             if self.param.integrator == "LFRA":
                 integ._scratch_io(False)
+        self._resident = False
+        if hasattr(self.io, "resident"):
+            self.io.resident = False
+        if hasattr(self.io, "flush"):
+            self.io.flush()
         self.progress()
         self.print_perf(_wall() - tic)
         self.finalize()

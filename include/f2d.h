@@ -111,6 +111,19 @@ int f2d_upload(f2d_ctx *ctx, const char *field, const double *h_src);
 int f2d_download(f2d_ctx *ctx, const char *field, double *h_dst);
 int f2d_field_ptr(f2d_ctx *ctx, const char *field, double **d_ptr);
 
+/* ---- observation points (model.py:48-51) --------------------------------- */
+/* io.write (io.py:12-32; NetCDF variables are float32, io.py:65): convert the
+ * field to float32 on the device and copy it to h_dst (pinned) on a separate
+ * copy stream, so the step loop is not stalled; f2d_io_sync waits for all
+ * outstanding history copies before the host reads h_dst. */
+int f2d_download_f32(f2d_ctx *ctx, const char *field, float *h_dst);
+int f2d_io_sync(f2d_ctx *ctx);
+/* diagnostics.Bulk.__call__ (diagnostics.py:39-62): the whole-array sums behind
+ * its ke / ens / vort / angular averages, one pass on the device (all-reduced
+ * over slabs).  out6 = [sum ke, sum omega^2, sum omega, sum U.y*xv, sum U.x*yu,
+ * sum msk];  row0 = first global row of this context's array (0 on one GPU). */
+int f2d_bulk_sums(f2d_ctx *ctx, int row0, double *out6);
+
 /* ---- time stepping ------------------------------------------------------ */
 /* RKIntegrator.step (integrators.py:76-79) with rk3/ef/enrk3 (:82-124):
  * nsteps fused steps at fixed dt, state stays on the device. */

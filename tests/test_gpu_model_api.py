@@ -211,3 +211,67 @@ def test_param_tracer_through_model(f2d, case):
                 model.step(1)
         ref = g.fields("final")[name]
         assert rel_l2(getattr(model.state, name), ref, model.mesh.msk) <= 1e-10, (case, resident)
+
+
+def test_device_observers_history_and_bulk(f2d, tmp_path, monkeypatch):
+    """Model.run() with nhis > 0 and diagnostics.Bulk: the history records are
+    float32 conversions done on the device + copy stream (f2d_download_f32) and
+    the bulk averages come from one device reduction (f2d_bulk_sums); both must
+    equal what the reference's host expressions give on the same states."""
+    monkeypatch.chdir(tmp_path)
+    from fluids2d_b200 import _nc
+    from fluids2d_b200.diagnostics import Bulk
+
+    def make(nhis):
+        p = f2d.Param()
+        p.nx, p.ny, p.dt, p.tend, p.maxite = 64, 48, 0.05, 1e9, 9
+        p.nhis, p.var_to_store = nhis, ["u", "omega", "p"]
+        m = f2d.Model(p)
+        x, y = m.mesh.xy()
+        m.mesh.msk[(x - 0.7) ** 2 + (y - 0.3) ** 2 < 0.1 ** 2] = 0
+        m.mesh.finalize()
+        set_initial_dipole(f2d, m, x0=0.4)
+        return m
+
+    # device path
+    m = make(3)
+    bulk = Bulk(m, ncfile="bulk_dev.nc")
+    m.diags.append(bulk)
+    assert not m._observation_due()                 # nothing here needs the host state
+    m.run()
+    assert m.time.ite == 9 and m.io.kt == 4          # records at ite 0, 3, 6, 9
+    dev = bulk.read()
+    # host path: same steps one by one through host buffers, observers fed host arrays
+    h = make(0)
+    hb = Bulk(h, ncfile="bulk_host.nc")
+    recs, stamps = [], []
+    for it in range(10):
+        if it % 3 == 0:
+            recs.append({k: np.array(a, dtype=np.float32) for k, a in
+                         (("ux", h.state.u.x), ("uy", h.state.u.y), ("omega", h.state.omega), ("p", h.state.p))})
+        if it < 9:
+            h.set_dt()
+            h.step(1)
+            hb()                                     # compute_diags follows each step (model.py:50)
+    hb.finalize()
+    host = hb.read()
+    with _nc.Dataset(m.param.outputfile, "r") as nc:
+        assert list(np.asarray(nc.variables["ite"][:])) == [0, 3, 6, 9]
+        for k in ("ux", "uy", "omega"):
+            got = np.asarray(nc.variables[k][:])
+            assert got.dtype.itemsize == 4 and got.shape == (4,) + m.mesh.shape
+            for r in range(4):
+                ref = recs[r][k]
+                assert np.abs(got[r] - ref).max() <= 2e-7 * max(np.abs(ref).max(), 1e-30), (k, r)
+    assert len(dev.time) == len(host.time) == 3
+    for name in ("ke", "ens", "vort", "angular"):
+        a, b = np.asarray(getattr(dev, name), float), np.asarray(getattr(host, name), float)
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-7 * np.abs(b).max() + 1e-30), name   # float32 file
+    # the sums themselves, in double
+    m.integrator.upload(m.state)
+    s = m.state
+    sums = m.mesh.engine.bulk_sums()
+    xv, yu = m.mesh.xy("y")[0], m.mesh.xy("x")[1]
+    ref = [s.ke.sum(), (s.omega ** 2).sum(), s.omega.sum(), (s.U.y * xv).sum(), (s.U.x * yu).sum(), m.mesh.msk.sum()]
+    for k in range(6):
+        assert abs(sums[k] - ref[k]) <= 1e-12 * max(abs(ref[k]), np.abs(s.ke).sum()), k
