@@ -63,6 +63,7 @@ SIGNATURES = {
     "f2d_field_ptr": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
     "f2d_download_f32": (_I, [_P, C.c_char_p, _P]),
     "f2d_io_sync": (_I, [_P]),
+    "f2d_set_forcing": (_I, [_P, C.c_char_p, _P, _D]),
     "f2d_bulk_sums": (_I, [_P, _I, C.POINTER(_D)]),
     "f2d_step": (_I, [_P, _D, _I]),
     "f2d_step_lfra": (_I, [_P, _D, _I, _D]),
@@ -279,6 +280,15 @@ class Engine:
         stream; io_sync() before reading it"""
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.size
         self._chk(self.lib.f2d_download_f32(self._h, self._n(name), _ptr(out)))
+
+    def set_forcing(self, leaf, pattern, amplitude=1.0):
+        """ds.<leaf> += amplitude * pattern in every stage; pattern None changes
+        only the amplitude"""
+        if pattern is not None:
+            pattern = np.ascontiguousarray(pattern, dtype=np.float64)
+            assert pattern.size == self.size
+        self._chk(self.lib.f2d_set_forcing(self._h, self._n(leaf), None if pattern is None else _ptr(pattern),
+                                           float(amplitude)))
 
     def io_sync(self):
         self._chk(self.lib.f2d_io_sync(self._h))

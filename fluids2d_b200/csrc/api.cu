@@ -155,6 +155,7 @@ int f2d_destroy(f2d_ctx *c) {
     for (auto &G : c->guess) for (double *g : G.g) cudaFree(g);
     for (auto &kv : c->mesh) cudaFree(kv.second);
     for (auto &kv : c->fields) cudaFree(kv.second);
+    for (auto &kv : c->forcing) cudaFree(kv.second.pattern);
     if (c->io_stream) cudaStreamSynchronize(c->io_stream);
     for (auto &kv : c->io_stage) {
         cudaFree(kv.second.d);
@@ -273,6 +274,11 @@ int f2d_download_f32(f2d_ctx *c, const char *field, float *h_dst) {
     F2D_TRY(find_field(c, field, &p));
     NEED(h_dst, "null destination");
     return download_f32(c, p, field, h_dst);
+}
+
+int f2d_set_forcing(f2d_ctx *c, const char *leaf, const double *h_pattern, double amplitude) {
+    NEED(c && leaf, "null argument");
+    return set_forcing(c, leaf, h_pattern, amplitude);
 }
 
 int f2d_io_sync(f2d_ctx *c) {

@@ -157,6 +157,9 @@ struct f2d_ctx {
     struct IoStage { float *d = nullptr; cudaEvent_t filled = nullptr, drained = nullptr; };
     std::map<std::string, IoStage> io_stage;
     cudaStream_t io_stream = nullptr;
+    // model.add_forcing with a device pattern: ds.<leaf> += amplitude * pattern
+    struct Forcing { double *pattern = nullptr; double amplitude = 0.0; };
+    std::map<std::string, Forcing> forcing;
     bool tracer = false;            // param.tracer: extra advected scalar "tracer" (equations.py:217-226)
     int guess_order = 4;            // 0 off, 1 previous step, 2 linear, 3 quadratic, 4 cubic ... 6
     int stage_hint = -1;
@@ -187,6 +190,7 @@ int model_step(f2d_ctx *c, double dt, int nsteps);
 int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma);
 int max_abs_U(f2d_ctx *c, double *out);
 int bulk_sums(f2d_ctx *c, int row0, double *out);
+int set_forcing(f2d_ctx *c, const std::string &leaf, const double *h_pattern, double amplitude);
 int download_f32(f2d_ctx *c, const double *src, const std::string &key, float *h_dst);
 // mg.cu
 int mg_build(f2d_ctx *c, int which);

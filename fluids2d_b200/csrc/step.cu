@@ -757,11 +757,64 @@ static std::string dsname(int k, const char *leaf) { return "ds" + std::to_strin
 
 static int model_rhs_core(f2d_ctx *c, int k);
 
+// ---------------------------------------------------------------------------
+// Forcing terms of the form  ds.<leaf> += amplitude * pattern  kept on the
+// device (model.add_forcing, model.py:121-123; addforcingterm,
+// equations.py:229-238: applied after the model's tendency, not filled).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_force(long n, double *__restrict__ ds, double *__restrict__ ustar, const double *__restrict__ F,
+        double amp, double cu) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double f = amp * F[k];
+    if (ds) ds[k] += f;
+    if (ustar) ustar[k] += cu * f;
+}
+
+// ds may be null (last fused stage: the tendency is not stored); ustar != null
+// adds cu * forcing to an already updated field (fused momentum stage)
+static int apply_forcing(f2d_ctx *c, const std::string &leaf, double *ds, double *ustar = nullptr, double cu = 0.0) {
+    auto it = c->forcing.find(leaf);
+    if (it == c->forcing.end() || it->second.amplitude == 0.0) return F2D_OK;
+    long n = (long)c->n;
+    k_force<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, ds, ustar, it->second.pattern,
+                                                               it->second.amplitude, cu);
+    c->launches++;
+    F2D_CUDA(cudaGetLastError());
+    return F2D_OK;
+}
+
+int set_forcing(f2d_ctx *c, const std::string &leaf, const double *h_pattern, double amplitude) {
+    if (std::find(c->prognostic.begin(), c->prognostic.end(), leaf) == c->prognostic.end()) {
+        set_error("forcing: '%s' is not a prognostic field of this model", leaf.c_str());
+        return F2D_ERR_ARG;
+    }
+    auto it = c->forcing.find(leaf);
+    if (!h_pattern && it == c->forcing.end()) {
+        set_error("forcing: no pattern set for '%s'", leaf.c_str());
+        return F2D_ERR_STATE;
+    }
+    if (h_pattern) {
+        f2d_ctx::Forcing &f = c->forcing[leaf];
+        if (!f.pattern) F2D_CUDA(cudaMalloc(&f.pattern, c->n * sizeof(double)));
+        F2D_CUDA(cudaMemcpyAsync(f.pattern, h_pattern, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        F2D_CUDA(cudaStreamSynchronize(c->stream));    // the host array may be pageable
+        f.amplitude = amplitude;
+    } else {
+        it->second.amplitude = amplitude;
+    }
+    return F2D_OK;
+}
+
 int model_rhs(f2d_ctx *c, int k) {
     if (!c->mesh_ready) { set_error("f2d_rhs before f2d_set_mask"); return F2D_ERR_STATE; }
     if (k < 0 || k >= c->nstages) { set_error("stage %d out of range", k); return F2D_ERR_ARG; }
     F2D_TRY(model_rhs_core(c, k));
-    return c->tracer ? tracer_rhs(c, k) : F2D_OK;
+    if (c->tracer) F2D_TRY(tracer_rhs(c, k));
+    for (const std::string &leaf : c->prognostic)
+        F2D_TRY(apply_forcing(c, leaf, c->f("ds" + std::to_string(k) + "." + leaf)));
+    return F2D_OK;
 }
 
 static int model_rhs_core(f2d_ctx *c, int k) {
@@ -1017,6 +1070,10 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     else if (nc == 2) F2D_TRY(STAGE(2));
     else F2D_TRY(STAGE(3));
 #undef STAGE
+    // momentum forcing: into the stored tendency and, scaled by this stage's own RK
+    // coefficient, into u* which the kernel above has already formed
+    F2D_TRY(apply_forcing(c, "u.x", rk.write_ds ? dux : nullptr, c->tmp[0], co[nc - 1]));
+    F2D_TRY(apply_forcing(c, "u.y", rk.write_ds ? duy : nullptr, c->tmp[1], co[nc - 1]));
     if (c->dist.on) {   // ghost rows of the updated velocity
         void *a[2] = {c->tmp[0], c->tmp[1]};
         F2D_TRY(dist_exchange(c, 2, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
@@ -1038,6 +1095,8 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     };
     if (bouss) F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
     if (c->tracer) F2D_TRY(tracer_rhs(c, s));
+    if (bouss) F2D_TRY(apply_forcing(c, "b", c->f(dsname(s, "b"))));
+    if (c->tracer) F2D_TRY(apply_forcing(c, "tracer", c->f(dsname(s, "tracer"))));
     if (bouss) F2D_TRY(update_scalar("b"));
     if (c->tracer) F2D_TRY(update_scalar("tracer"));
     return model_diag_impl(c, true);

@@ -57,6 +57,8 @@ class RKIntegrator:
         self.rhs = self._device_rhs
         self.diag = self._diag_on_device
         self._fields = None
+        self.device_forcings = []      # equations.DeviceForcing objects (Model.add_forcing)
+        self.time = None
 
     # ---- host <-> device ----------------------------------------------------
     def _names(self, state):
@@ -120,9 +122,14 @@ class RKIntegrator:
         skip = {"div", "flx.x", "flx.y", "vomega", "work"} | ({"U.x", "U.y"} if has_u else set())
         return [n for n in self._names(state) if n not in skip]
 
+    def _update_forcings(self, t):
+        for f in self.device_forcings:
+            f.update(self.engine, t)
+
     def step(self, state, time):
         if self.rhs is self._device_rhs:
             self.upload(state, self._step_inputs(state))
+            self._update_forcings(time.t)
             self.engine.step(time.dt, 1)
             self.download(state)
         else:
@@ -133,6 +140,13 @@ class RKIntegrator:
         """device-only step(s): the caller guarantees the device state is current"""
         if self.rhs is not self._device_rhs:
             raise RuntimeError("a host forcing is installed: use step()")
+        if self.device_forcings and self.time is not None:
+            # the amplitude follows the clock: one call per step, t as the reference's
+            # callback would read it (constant within a step)
+            for k in range(nsteps):
+                self._update_forcings(self.time.t + k * dt)
+                self.engine.step(dt, 1)
+            return
         self.engine.step(dt, nsteps)
 
     def _step_with_host_rhs(self, state, dt):
@@ -166,6 +180,8 @@ class LFRAintegrator(RKIntegrator):
         self.rhs = self._device_rhs
         self.diag = self._diag_on_device
         self._fields = None
+        self.device_forcings = []      # equations.DeviceForcing objects (Model.add_forcing)
+        self.time = None
 
     def _scratch_io(self, upload):
         e = self.engine
@@ -179,6 +195,8 @@ class LFRAintegrator(RKIntegrator):
             raise NotImplementedError("host forcing with the LFRA integrator is not on the device path")
         self.upload(state, self._step_inputs(state))
         self._scratch_io(True)
+        for f in self.device_forcings:
+            f.update(self.engine, time.t)
         self.engine.step_lfra(time.dt, time.ite == 0, self.RAgamma)
         self.download(state)
         self._scratch_io(False)
@@ -186,6 +204,9 @@ class LFRAintegrator(RKIntegrator):
 
     def step_resident(self, dt, nsteps=1, first=False):
         for k in range(nsteps):
+            if self.time is not None:
+                for f in self.device_forcings:
+                    f.update(self.engine, self.time.t + k * dt)
             self.engine.step_lfra(dt, first and k == 0, self.RAgamma)
 
 

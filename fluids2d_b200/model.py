@@ -4,7 +4,7 @@ import signal
 from time import time as _wall
 
 from . import weno as _weno
-from .equations import addforcingterm
+from .equations import DeviceForcing, addforcingterm
 from .integrators import get_integrator
 from .io import IO
 from .meshes import Mesh
@@ -25,6 +25,7 @@ class Model:
         self.state = State(param, self.mesh.shape)
         self.set_integrator()
         self.time = Time(param)
+        self.integrator.time = self.time      # time-dependent device forcings read the clock
         self.io = IO(param, self.mesh, self.state, self.time)
         self._resident = False        # True while run() keeps the state on the device
         self.callbacks = []
@@ -163,4 +164,13 @@ class Model:
             d()
 
     def add_forcing(self, forcing):
-        self.integrator.rhs = addforcingterm(self.param, self.mesh, self.integrator.rhs, forcing)
+        """model.py:121-123.  A host callable wraps ``integrator.rhs`` (the step then
+        runs stage by stage through host buffers); an ``equations.DeviceForcing``
+        is installed on the device and keeps the fused resident step."""
+        integ = self.integrator
+        if isinstance(forcing, DeviceForcing) and integ.rhs is integ._device_rhs:
+            print("[INFO] add a forcing term (device)")
+            forcing.install(self.mesh.engine, self.time.t)
+            integ.device_forcings.append(forcing)
+            return
+        integ.rhs = addforcingterm(self.param, self.mesh, integ.rhs, forcing)

@@ -111,6 +111,15 @@ int f2d_upload(f2d_ctx *ctx, const char *field, const double *h_src);
 int f2d_download(f2d_ctx *ctx, const char *field, double *h_dst);
 int f2d_field_ptr(f2d_ctx *ctx, const char *field, double **d_ptr);
 
+/* Model.add_forcing (model.py:121-123; addforcingterm, equations.py:229-238) for
+ * forcings of the form  ds.<leaf> += amplitude * pattern  (forced_convection.py:
+ * 9-24): the pattern (n2*n1 doubles, host) is kept on the device and added after
+ * the model's tendency in every stage of f2d_step / f2d_rhs, so a forced run
+ * needs no host round trip.  h_pattern == NULL only changes the amplitude
+ * (time-dependent coefficient, set once per step); amplitude 0 disables it.
+ * leaf must be a prognostic field ("u.x", "b", "h", "tracer", ...). */
+int f2d_set_forcing(f2d_ctx *ctx, const char *leaf, const double *h_pattern, double amplitude);
+
 /* ---- observation points (model.py:48-51) --------------------------------- */
 /* io.write (io.py:12-32; NetCDF variables are float32, io.py:65): convert the
  * field to float32 on the device and copy it to h_dst (pinned) on a separate

@@ -275,3 +275,70 @@ def test_device_observers_history_and_bulk(f2d, tmp_path, monkeypatch):
     ref = [s.ke.sum(), (s.omega ** 2).sum(), s.omega.sum(), (s.U.y * xv).sum(), (s.U.x * yu).sum(), m.mesh.msk.sum()]
     for k in range(6):
         assert abs(sums[k] - ref[k]) <= 1e-12 * max(abs(ref[k]), np.abs(s.ke).sum()), k
+
+
+def test_device_forcing_equals_host_callback_and_oracle(f2d):
+    """equations.DeviceForcing (ds.<field> += amplitude(t) * pattern, the shape of
+    forced_convection.py:9-24) keeps the fused resident step; the same object used
+    as a HOST callback (reference granularity) and in the CPU oracle must give the
+    same fields.  Covers a scalar (b), the momentum (u.x) and a time-dependent
+    amplitude."""
+    from types import SimpleNamespace
+    from oracle import fluids2d_oracle as orc
+    from fluids2d_b200.equations import DeviceForcing
+    g = Golden("warm_bubble")
+    nsteps, dt = 4, g.dts[0]
+
+    def make_forcing(mesh):
+        x, y = mesh.xy()
+        Fb = 0.3 * np.exp(-((x - 1.0) ** 2 + (y - 0.2) ** 2) / 0.02) * mesh.msk
+        Fu = 0.05 * np.sin(2 * np.pi * y) * mesh.mskx
+        return DeviceForcing({"b": Fb, "u": (Fu, np.zeros_like(Fu))}, amplitude=lambda t: 1.0 + 4.0 * t)
+
+    def fresh():
+        p = f2d.Param()
+        for k, v in g.param.items():
+            setattr(p, k, v)
+        p.dt = dt
+        m = f2d.Model(p)
+        set_state(m.state, g.fields("init"))
+        return m
+
+    dev, host, free = fresh(), fresh(), fresh()
+    dev.add_forcing(make_forcing(dev.mesh))
+    assert dev.integrator.rhs is dev.integrator._device_rhs        # still the fused path
+    host.mesh.time = host.time                                     # forced_convection.py:6
+    fh = make_forcing(host.mesh)
+    host.add_forcing(lambda param, mesh, s, ds: fh(param, mesh, s, ds))
+    assert host.integrator.rhs is not host.integrator._device_rhs
+    # device forcing, resident steps
+    dev.integrator.upload(dev.state)
+    for k in range(nsteps):
+        dev.integrator.step_resident(dt, 1)
+        dev.time.pushforward()
+    dev.integrator.download(dev.state)
+    for m in (host, free):
+        m.set_dt()
+        m.step(nsteps)
+    # oracle with the same callback
+    om = orc.Model(orc.make_param(**dict(g.param, dt=dt)), msk=g.msk.copy())
+    set_state(om.state, g.fields("init"))
+    clock = SimpleNamespace(t=0.0)
+    om.mesh.time = clock
+    fo = make_forcing(SimpleNamespace(xy=dev.mesh.xy, msk=g.msk, mskx=dev.mesh.mskx))
+    plain_rhs = om.rhs
+
+    def forced(s, ds):
+        plain_rhs(s, ds)
+        fo(om.param, om.mesh, s, ds)
+    om.rhs = forced
+    for k in range(nsteps):
+        clock.t = k * dt
+        om.step(dt)
+    for name, w in (("b", dev.mesh.msk), ("u.x", dev.mesh.mskx), ("u.y", dev.mesh.msky), ("omega", dev.mesh.mskv)):
+        n, c = (name.split(".") + [None])[:2]
+        get = lambda s: getattr(getattr(s, n), c) if c else getattr(s, n)
+        a, b, o, f = get(dev.state), get(host.state), get(om.state), get(free.state)
+        assert rel_l2(a, o, w) <= 1e-10, ("device vs oracle", name, rel_l2(a, o, w))
+        assert rel_l2(b, o, w) <= 1e-10, ("host callback vs oracle", name)
+        assert rel_l2(a, f, w) > 1e-4, ("the forcing must matter", name)
