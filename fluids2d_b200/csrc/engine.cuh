@@ -126,6 +126,8 @@ struct Multigrid {
 namespace f2d {
 struct GuessHistory {            // last solutions of one RK stage's elliptic solve
     double *g[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double t[6] = {0, 0, 0, 0, 0, 0};     // model time and step length each was computed at
+    double dt[6] = {1, 1, 1, 1, 1, 1};
     int valid = 0;
 };
 }  // namespace f2d
@@ -160,6 +162,7 @@ struct f2d_ctx {
     // model.add_forcing with a device pattern: ds.<leaf> += amplitude * pattern
     struct Forcing { double *pattern = nullptr; double amplitude = 0.0; };
     std::map<std::string, Forcing> forcing;
+    double sim_t = 0.0, sim_dt = 1.0;   // clock of f2d_step: start of the current step, its length
     bool tracer = false;            // param.tracer: extra advected scalar "tracer" (equations.py:217-226)
     int guess_order = 4;            // 0 off, 1 previous step, 2 linear, 3 quadratic, 4 cubic ... 6
     int stage_hint = -1;

@@ -713,20 +713,31 @@ __global__ void __launch_bounds__(256) k_guess(long n, double *__restrict__ x, G
     x[k] = v;
 }
 
-// polynomial extrapolation through the last `order` solutions of this stage
-// (equal steps): x0 = sum_k (-1)^(k+1) C(order, k) g_k
-static int guess_before(f2d_ctx *c, int stage, double *x) {
+// Polynomial extrapolation in model time through the last `order` solutions of
+// this stage: Lagrange weights for the nodes t_k evaluated at the current step's
+// time (equal steps: the alternating binomials 4, -6, 4, -1 ...).  The pressure
+// of the incremental RK form is proportional to the step length (u is already
+// divergence free, only the dt-scaled increment is projected), so with
+// scale_dt the smooth quantity p / dt is what gets extrapolated -- an adaptive
+// dt (model.py:71-87) then costs no accuracy.
+static int guess_before(f2d_ctx *c, int stage, double *x, bool scale_dt) {
     if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
     GuessHistory &G = c->guess[stage];
     int order = std::min(G.valid, std::min(c->guess_order, 6));
     if (order <= 0) return F2D_OK;
+    const double tn = c->sim_t;
+    if (!(tn > G.t[0])) return F2D_OK;        // not a later time (dt <= 0): keep what x holds
+    for (int k = 1; k < order; k++)           // nodes must be strictly ordered in time
+        if (!(G.t[k - 1] > G.t[k])) { order = k; break; }
     GuessArgs A;
     A.n = order;
-    double binom = 1.0;
-    for (int k = 1; k <= order; k++) {
-        binom = binom * (order - k + 1) / k;
-        A.g[k - 1] = G.g[k - 1];
-        A.w[k - 1] = (k & 1) ? binom : -binom;
+    for (int k = 0; k < order; k++) {
+        double w = 1.0;
+        for (int m = 0; m < order; m++)
+            if (m != k) w *= (tn - G.t[m]) / (G.t[k] - G.t[m]);
+        if (scale_dt) w *= c->sim_dt / G.dt[k];
+        A.g[k] = G.g[k];
+        A.w[k] = w;
     }
     for (int k = order; k < 6; k++) { A.g[k] = nullptr; A.w[k] = 0.0; }
     long n = (long)c->n;
@@ -747,7 +758,10 @@ static int guess_after(f2d_ctx *c, int stage, const double *x) {
     // rotate: g3 <- g2 <- g1 <- x
     double *last = G.g[depth - 1];
     for (int k = depth - 1; k > 0; k--) G.g[k] = G.g[k - 1];
+    for (int k = depth - 1; k > 0; k--) { G.t[k] = G.t[k - 1]; G.dt[k] = G.dt[k - 1]; }
     G.g[0] = last;
+    G.t[0] = c->sim_t;
+    G.dt[0] = c->sim_dt;
     F2D_CUDA(cudaMemcpyAsync(G.g[0], x, c->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     G.valid = std::min(G.valid + 1, 6);
     return F2D_OK;
@@ -846,7 +860,7 @@ static int model_rhs_core(f2d_ctx *c, int k) {
         k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, dux, duy, dh, c->m("slip"), c->m("mskv"),
                                                       mf0H, c->f("pv"));
         LAUNCH_CHECK(c);
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi")));
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi"), false));
         F2D_TRY(mg_solve(c, F2D_SOLVER_HELMHOLTZ, c->f("pv"), 1.0, c->f("psi"), nullptr, nullptr));
         F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
         double f0ag = c->cfg.f0 * c->area / c->cfg.g;
@@ -948,7 +962,7 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->tmp[0], c->tmp[1], c->m("msk"), c->f("div"));
         LAUNCH_CHECK(c);
         // A p = -delta * area       (operators.py:117)
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("p")));
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("p"), true));
         F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
         F2D_TRY(guess_after(c, c->stage_hint, c->f("p")));
         F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
@@ -972,7 +986,7 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         k_c2v<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f(qg ? "pv" : "omega"), c->hb, qg ? c->cfg.f0 / +c->cfg.H : 0.0,
                                                      c->m("mskv"), rhs);
         LAUNCH_CHECK(c);
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi")));
+        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi"), false));
         F2D_TRY(mg_solve(c, qg ? F2D_SOLVER_HELMHOLTZ : F2D_SOLVER_VERTICES, rhs, 1.0, c->f("psi"), nullptr, nullptr));
         F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
         // perpgrad(..., contravariant=True): u.x *= 1/dy**2, u.y *= 1/dx**2
@@ -1148,6 +1162,7 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
     if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
     if (c->cfg.integrator == F2D_INT_LFRA) { set_error("LFRA steps go through f2d_step_lfra"); return F2D_ERR_STATE; }
     for (int it = 0; it < nsteps; it++) {
+        c->sim_dt = dt;
         for (int s = 0; s < c->nstages; s++) {
             double co[3];
             int nc = rk_coefs(c->cfg.integrator, dt, s, co);
@@ -1163,6 +1178,7 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
             c->stage_hint = -1;
             F2D_TRY(st);
         }
+        c->sim_t += dt;
     }
     return F2D_OK;
 }
