@@ -142,6 +142,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     F2D_CUDA(cudaMalloc(&c->d_count, sizeof(unsigned int)));
     F2D_CUDA(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned int), c->stream));
     F2D_CUDA(cudaMallocHost(&c->h_scal, 32 * sizeof(double)));
+    F2D_CUDA(cudaMallocHost(&c->h_hist, 512 * sizeof(double)));
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     return F2D_OK;
 }
@@ -169,6 +170,7 @@ int f2d_destroy(f2d_ctx *c) {
     cudaFree(c->d_part);
     cudaFree(c->d_count);
     cudaFreeHost(c->h_scal);
+    cudaFreeHost(c->h_hist);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);

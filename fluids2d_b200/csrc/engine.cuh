@@ -115,6 +115,7 @@ struct Multigrid {
     const double *gx[3] = {nullptr, nullptr, nullptr};
     int64_t glaunches[3] = {0, 0, 0}, gexchanges[3] = {0, 0, 0};
     bool warm = false;
+    int expect = 0;        // iterations the previous solve needed: that many run without a host check
     double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr;   // CG vectors (n2,n1)
     float *zf = nullptr, *zf2 = nullptr;   // preconditioned residual z = M r: fp32 (mg_tiles.cuh)
     int tail = 1;                     // first level handled by the single-CTA tail kernel
@@ -172,6 +173,7 @@ struct f2d_ctx {
     size_t part_capacity = 0;       // doubles
     unsigned int *d_count = nullptr;
     double *h_scal = nullptr;       // pinned mirror
+    double *h_hist = nullptr;       // pinned: (rr, sum r) of the PCG iterations that ran unchecked
     // solver statistics
     int64_t nsolves = 0, niters = 0;
     double max_relres = 0;

@@ -1492,7 +1492,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
     const double N = M.n_global, inv_n = 1.0 / N;
     double *S = c->d_scal;
-    int it = 0;
+    int it = 0, first_ok = 0;   // first_ok: an unchecked iteration that had already converged
     double relres = 0.0;
     bool conv = false;
     auto projected = [&](double rr, double sum) { return singular ? std::max(rr - sum * sum * inv_n, 0.0) : rr; };
@@ -1560,6 +1560,11 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         };
         static const bool no_graph = getenv("F2D_NO_GRAPH") != nullptr;
         const bool use_graph = !no_graph && !unfused && M.warm;
+        // The previous solve of this system needed M.expect iterations (the
+        // first guess makes consecutive solves alike): run that many back to
+        // back, recording their residual norms asynchronously, and only then
+        // take the host round trip that decides convergence.
+        const int nocheck = (use_graph && !debug && M.expect > 1) ? std::min(M.expect - 1, 255) : 0;
         for (it = 0; !conv && it < maxit; it++) {
             const int cls = it == 0 ? 0 : ((it & 1) ? 1 : 2);
             if (use_graph) {
@@ -1589,7 +1594,17 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 F2D_TRY(iteration(it, pold, pnew));
             }
             std::swap(pold, pnew);
+            if (it < nocheck && it + 1 < maxit) {
+                F2D_CUDA(cudaMemcpyAsync(c->h_hist + 2 * it, S + S_RR, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+                continue;
+            }
             F2D_TRY(read_scalars(c, S_RR, 2));
+            if (nocheck > 0 && it == nocheck)        // what the unchecked iterations did
+                for (int j = 0; j < nocheck && !first_ok; j++) {
+                    double rj = std::sqrt(projected(c->h_hist[2 * j], c->h_hist[2 * j + 1]) / ff);
+                    if (!(rj > rtol)) first_ok = j + 1;
+                    best = std::min(best, rj);
+                }
             relres = std::sqrt(projected(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff);
             if (debug) fprintf(stderr, "[f2d]   it %d relres %.3e\n", it + 1, relres);
             if (!(relres > rtol)) { conv = true; it++; break; }
@@ -1598,6 +1613,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         }
     }
     M.warm = true;      // every kernel attribute is set by now: later solves may capture graphs
+    if (!plain) M.expect = conv ? (first_ok ? first_ok : it) : 0;
     c->nsolves++;
     c->niters += it;
     c->max_relres = std::max(c->max_relres, relres);
