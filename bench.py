@@ -324,7 +324,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=6,
+                    help="untimed steps; the first-guess history of the elliptic solves (4 steps deep) fills during them")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", dest="n", type=int, default=4096, help="grid size n (default: the headline 4096)")
     ap.add_argument("--cpu-n", type=int, default=512, help="grid of the bounded CPU sample")
