@@ -292,7 +292,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "clocks": summarize_clocks(samples), "finite": ok,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -308,7 +308,7 @@ def run_reference(args):
     sample = (f"oracle port of the reference CPU path (numpy + C WENO kernels + scipy SuperLU), Euler "
               f"{n}^2 x-periodic as a bounded sample of the 4096^2 workload (the reference's LU cannot "
               f"reach 4096^2); {sps:.3f} s/step; LU set-up {setup:.1f} s not counted")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": min(args.warmup, 1),
         "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,10 +317,31 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_json_out = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL
+    prints its version banner on stdout when NCCL_DEBUG is WARN or VERSION), so
+    keep a private handle on the real stdout for the JSON line and point fd 1 --
+    and with it every other writer in the process -- at stderr."""
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
