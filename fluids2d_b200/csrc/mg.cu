@@ -1203,6 +1203,13 @@ static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, i
 // in place, the tile kernels write their up leg to the second buffer
 static const CT *level_result(const Multigrid &M, int l) { return l >= M.tail ? M.lev[l].x : M.lev[l].x2; }
 
+// F2D_NO_OPEN=1: every tile takes the generic (masked) path -- A/B timing and the
+// test that both paths give the same bits
+static int allow_open_tiles() {
+    static const int v = getenv("F2D_NO_OPEN") == nullptr;
+    return v;
+}
+
 // fine-level legs.  FT = float: the CG preconditioner (z = M r) relaxes in fp32
 // on the fp64 residual and stores z in fp32; FT = double: plain V-cycles on x itself.
 template <typename FT, int NU, bool ZERO>
@@ -1217,7 +1224,7 @@ static int launch_down0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const
     dim3 g((F.nx + TI - 1) / TI, (F.ny + TJ - 1) / TJ);
     const Level &C = M.lev[1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / M.n_global,
-                                               C.ny, C.nx, C.pitch, C.b);
+                                               DownArgs{C.ny, C.nx, C.pitch, allow_open_tiles()}, C.b);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -1235,8 +1242,8 @@ static int launch_up0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const d
     if (DOT && (size_t)g.x * g.y * 2 > c->part_capacity) { set_error("reduction scratch too small"); return F2D_ERR_STATE; }
     const Level &C = M.lev[1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / M.n_global,
-                                               C.ny, C.nx, C.pitch, F.periodic, level_result(M, 1), c->d_part, c->d_count,
-                                               c->d_scal + S_RZNEW);
+                                               UpArgs{C.ny, C.nx, C.pitch, F.periodic, allow_open_tiles()},
+                                               level_result(M, 1), c->d_part, c->d_count, c->d_scal + S_RZNEW);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -1252,7 +1259,8 @@ static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
     const Level &C = M.lev[l + 1];
-    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x, Lv.b, 1.0, c->d_scal, -1, 0.0, C.ny, C.nx, C.pitch, C.b);
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x, Lv.b, 1.0, c->d_scal, -1, 0.0,
+                                               DownArgs{C.ny, C.nx, C.pitch, 0}, C.b);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -1268,8 +1276,9 @@ static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     if (!once) { F2D_TRY(set_smem(kern, smem)); once = true; }
     dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
     const Level &C = M.lev[l + 1];
-    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x2, Lv.b, 1.0, c->d_scal, -1, 0.0, C.ny, C.nx, C.pitch,
-                                               M.fine.periodic, level_result(M, l + 1), nullptr, nullptr, nullptr);
+    kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x2, Lv.b, 1.0, c->d_scal, -1, 0.0,
+                                               UpArgs{C.ny, C.nx, C.pitch, M.fine.periodic, 0}, level_result(M, l + 1),
+                                               nullptr, nullptr, nullptr);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }

@@ -27,6 +27,16 @@
 //
 // FINE  (level 0): fp64, operator from one byte of mask bits per point
 // COARSE (l >= 1): CT (fp32) arrays of face couplings and inverse diagonals.
+//
+// OPEN tiles.  The tile kernels are instruction-issue bound, and half of their
+// instructions are bounds tests, periodic wraps and mask-bit look-ups that only
+// matter next to a wall.  A CTA whose whole window lies inside the array and
+// whose mask bytes are all 0xFF (every point an unknown, every face open, every
+// parent fluid -- the vast majority of tiles of any domain) takes a path
+// without them: constant diagonal, constant prolongation weight, unconditional
+// stores.  The decision is block-uniform (__syncthreads_and); both paths round
+// identically (explicit _rn intrinsics below), so the result does not depend
+// on which tiles are open, on the tiling, or on the slab decomposition.
 #pragma once
 #include "engine.cuh"
 #include "reduce.cuh"
@@ -47,6 +57,32 @@ struct CoarseArrays {       // level l >= 1, halo-padded (ny+2) x pitch
     const T *cx, *cy, *dinv;
     const uint8_t *code;
 };
+
+// sum of the four neighbour contributions / Gauss-Seidel update / residual with
+// explicit roundings: the generic and the open-tile path give the same bits
+__device__ __forceinline__ float nb_sum(float cx, float cy, float xw, float xe, float xs, float xn) {
+    return __fmaf_rn(cx, __fadd_rn(xw, xe), __fmul_rn(cy, __fadd_rn(xs, xn)));
+}
+__device__ __forceinline__ double nb_sum(double cx, double cy, double xw, double xe, double xs, double xn) {
+    return __fma_rn(cx, __dadd_rn(xw, xe), __dmul_rn(cy, __dadd_rn(xs, xn)));
+}
+__device__ __forceinline__ float gs_new(float f, float off, float dinv) { return __fmul_rn(__fadd_rn(f, off), dinv); }
+__device__ __forceinline__ double gs_new(double f, double off, double dinv) { return __dmul_rn(__dadd_rn(f, off), dinv); }
+// (f - (diag x - off)) * w
+__device__ __forceinline__ float res_val(float f, float diag, float x, float off, float w) {
+    return __fmul_rn(__fsub_rn(f, __fsub_rn(__fmul_rn(diag, x), off)), w);
+}
+__device__ __forceinline__ double res_val(double f, double diag, double x, double off, double w) {
+    return __dmul_rn(__dsub_rn(f, __dsub_rn(__dmul_rn(diag, x), off)), w);
+}
+__device__ __forceinline__ float prol_val(float x00, float xn0, float x0n, float xnn) {
+    return __fadd_rn(__fmaf_rn(3.0f, __fadd_rn(xn0, x0n), __fmul_rn(9.0f, x00)), xnn);
+}
+__device__ __forceinline__ double prol_val(double x00, double xn0, double x0n, double xnn) {
+    return __dadd_rn(__fma_rn(3.0, __dadd_rn(xn0, x0n), __dmul_rn(9.0, x00)), xnn);
+}
+__device__ __forceinline__ float mul_add(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double mul_add(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 __device__ __forceinline__ int wrap_mod(int i, int n) {
     i %= n;
@@ -83,6 +119,13 @@ struct FineLevel {
         int ai = F.oi + i;
         return (ai < 0 || ai >= F.n1) ? -1 : i;
     }
+    // the window [j0, j0+nj) x [i0, i0+ni) needs no bounds test and no wrap
+    __device__ __forceinline__ bool inside(int j0, int i0, int nj, int ni) const {
+        return j0 >= 0 && j0 + nj <= F.ny && F.oj + j0 >= 0 && F.oj + j0 + nj <= F.n2 &&
+               i0 >= 0 && i0 + ni <= F.nx && F.oi + i0 >= 0 && F.oi + i0 + ni <= F.n1;
+    }
+    __device__ __forceinline__ long base(int j, int i) const { return (long)(F.oj + j) * F.n1 + F.oi + i; }
+    __device__ __forceinline__ int stride() const { return F.n1; }
 };
 
 template <typename T>
@@ -101,6 +144,9 @@ struct CoarseLevel {
         if (A.periodic) return wrap_col(i, A.nx);
         return (i < 0 || i >= A.nx) ? -1 : i;
     }
+    __device__ __forceinline__ bool inside(int, int, int, int) const { return false; }   // generic path only
+    __device__ __forceinline__ long base(int j, int i) const { return (long)(j + 1) * A.pitch + 1 + i; }
+    __device__ __forceinline__ int stride() const { return A.pitch; }
 };
 
 // ---- shared-memory window -----------------------------------------------------
@@ -157,8 +203,10 @@ struct Window {
     // A warp owns rows a0, a0+16, ... which all have the parity of a0, so the
     // column offset o, the bounds test and every neighbour offset are hoisted;
     // the unrolled body is loads at constant offsets from one base pointer.
-    template <bool NO_NEIGHBOURS>
-    __device__ __forceinline__ void relax(int col, int m, int par0) {
+    // OPEN (FINE only): every point of the window is an unknown with four open
+    // faces -> constant inverse diagonal dinv0, no mask look-up.
+    template <bool NO_NEIGHBOURS, bool OPEN>
+    __device__ __forceinline__ void relax(int col, int m, int par0, T dinv0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
         const int a0 = m + warp;
         const int o = col ^ ((par0 + a0) & 1), b = 2 * k + o;
@@ -171,20 +219,21 @@ struct Window {
 #pragma unroll
         for (int r = 0; r < ROWS_PER_WARP; r++) {
             if (r >= nrow) break;
-            T acc = fp[r * S];
+            T off = T(0);
             if (!NO_NEIGHBOURS) {
                 const T *q = xq + r * S;
                 T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
-                if constexpr (FINE) acc += cxf * (xw + xe) + cyf * (xs + xn);
-                else acc += CX[p0 + r * S] * xw + CX[q0 + o + r * S] * xe + CY[p0 + r * S] * xs + CY[q0 + TK + r * S] * xn;
+                if constexpr (FINE) off = nb_sum(cxf, cyf, xw, xe, xs, xn);
+                else off = CX[p0 + r * S] * xw + CX[q0 + o + r * S] * xe + CY[p0 + r * S] * xs + CY[q0 + TK + r * S] * xn;
             }
-            if constexpr (FINE) xp[r * S] = acc * tab_dinv[B[p0 + r * S] & 31];
-            else xp[r * S] = acc * DI[p0 + r * S];
+            if constexpr (FINE) xp[r * S] = gs_new(fp[r * S], off, OPEN ? dinv0 : tab_dinv[B[p0 + r * S] & 31]);
+            else xp[r * S] = (fp[r * S] + off) * DI[p0 + r * S];
         }
     }
 
     // residual, pre-multiplied by 1/normaliser of the prolongation, into Fv (ring m)
-    __device__ __forceinline__ void residual(int m, int par0) {
+    template <bool OPEN>
+    __device__ __forceinline__ void residual(int m, int par0, T diag0, T invw0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
         const int a0 = m + warp;
         const int rp = (par0 + a0) & 1;
@@ -201,17 +250,22 @@ struct Window {
                 const int p = p0 + r * S;
                 const T *q = X + q0 + r * S;
                 T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
-                uint8_t bits = B[p];
-                T off, diag;
-                if constexpr (FINE) {
-                    off = cxf * (xw + xe) + cyf * (xs + xn);
-                    diag = tab_diag[bits & 31];
+                T res;
+                if constexpr (FINE && OPEN) {
+                    res = res_val(Fv[p], diag0, X[p], nb_sum(cxf, cyf, xw, xe, xs, xn), invw0);
                 } else {
-                    off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
-                    T di = DI[p];
-                    diag = di != T(0) ? T(1) / di : T(0);
+                    uint8_t bits = B[p];
+                    T off, diag;
+                    if constexpr (FINE) {
+                        off = nb_sum(cxf, cyf, xw, xe, xs, xn);
+                        diag = tab_diag[bits & 31];
+                    } else {
+                        off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
+                        T di = DI[p];
+                        diag = di != T(0) ? T(1) / di : T(0);
+                    }
+                    res = (bits & NB_SELF) ? res_val(Fv[p], diag, X[p], off, tab_invw[bits >> 5]) : T(0);
                 }
-                T res = (bits & NB_SELF) ? (Fv[p] - (diag * X[p] - off)) * tab_invw[bits >> 5] : T(0);
                 Fv[p] = res;    // each thread only overwrites what it alone reads
             }
         }
@@ -270,7 +324,7 @@ struct Window {
                 if constexpr (FINE) {
                     // masked entries of the field arrays may hold anything: select, do not multiply
                     // (the residual is scaled and shifted in fp64 before it is narrowed)
-                    Fv[p] = self ? (T)(fscale * (double)fv[r][h] - fshift) : T(0);
+                    Fv[p] = self ? (T)__fma_rn(fscale, (double)fv[r][h], -fshift) : T(0);
                     X[p] = self ? (T)xv[r][h] : T(0);
                 } else {
                     Fv[p] = (T)fv[r][h];
@@ -279,6 +333,48 @@ struct Window {
                 }
             }
         }
+    }
+
+    // FINE, window wholly inside the array (Lev::inside): the same load without
+    // bounds tests or wraps.  Fills the window exactly as load() does and returns
+    // whether every mask byte this thread saw is 0xFF.
+    template <bool LOAD_X, class Lev, typename TX, typename TF>
+    __device__ __forceinline__ bool load_inside(const Lev &L, const TX *__restrict__ xin, const TF *__restrict__ fin,
+                                                double fscale, double fshift, int wj0, int wi0, int par0) {
+        static_assert(FINE, "open tiles exist on the fine level only");
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        constexpr int R = WJ / TILE_WARPS;
+        const long g0 = L.base(wj0 + warp, wi0 + 2 * k);
+        const long st = (long)TILE_WARPS * L.stride();
+        TF fv[R][2];
+        TX xv[R][2];
+        uint8_t bits[R][2];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long g = g0 + r * st + h;
+                bits[r][h] = L.F.nb[g];
+                fv[r][h] = fin[g];
+                xv[r][h] = TX(0);
+                if (LOAD_X) xv[r][h] = xin[g];
+            }
+        }
+        unsigned all = 0xFFu;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int a = warp + r * TILE_WARPS, rp = (par0 + a) & 1;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int p = at(rp ^ h, a, k);
+                bool self = bits[r][h] & NB_SELF;
+                all &= bits[r][h];
+                B[p] = bits[r][h];
+                Fv[p] = self ? (T)__fma_rn(fscale, (double)fv[r][h], -fshift) : T(0);
+                X[p] = self ? (T)xv[r][h] : T(0);
+            }
+        }
+        return all == 0xFFu;
     }
 };
 
@@ -291,38 +387,47 @@ struct Window {
 // ---------------------------------------------------------------------------
 //   TX / TF: storage types of x and f in global memory (the fine level of the
 //          CG preconditioner relaxes in fp32 on an fp64 residual)
-template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
-k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
-          const double *__restrict__ scal, int sumr_slot, double inv_n,
-          int nyc, int nxc, int pitchc, TC *__restrict__ bc) {
+struct DownArgs {
+    int nyc, nxc, pitchc;   // next coarser level
+    int allow_open;         // 0: every tile takes the generic path (F2D_NO_OPEN, A/B tests)
+};
+
+// everything after the window is loaded; OPEN: see the header comment
+template <bool OPEN, typename T, typename TX, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
+__device__ __forceinline__ void down_body(Window<T, FINE, WJ> &W, const Lev &L, TX *__restrict__ xout,
+                                          const DownArgs &A, TC *__restrict__ bc, int tj0, int ti0) {
     constexpr int H = halo_down(NU, ZERO);
     constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
-    extern __shared__ __align__(16) unsigned char smem[];
-    Window<T, FINE, WJ> W;
-    W.carve(smem);
-    const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-    double fshift = 0.0;
-    if constexpr (FINE) {
-        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        W.fill_tables(&L.F, L.dirichlet());
-        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
-    } else W.fill_tables(nullptr, L.dirichlet());
-    W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-    __syncthreads();
+    T dinv0 = T(0), diag0 = T(0), invw0 = T(0);
+    if constexpr (OPEN) { dinv0 = W.tab_dinv[31]; diag0 = W.tab_diag[31]; invw0 = W.tab_invw[7]; }
     // ---- NU sweeps, red then black
 #pragma unroll
     for (int hs = 0; hs < 2 * NU; hs++) {
-        if (ZERO && hs == 0) W.template relax<true>(0, 0, par0);
-        else W.template relax<false>(hs & 1, ZERO ? hs : hs + 1, par0);
+        if (ZERO && hs == 0) W.template relax<true, OPEN>(0, 0, par0, dinv0);
+        else W.template relax<false, OPEN>(hs & 1, ZERO ? hs : hs + 1, par0, dinv0);
         __syncthreads();
     }
     // ---- residual on the tile +- 1, then write x and the restricted residual
-    W.residual(H - 1, par0);
-    {
+    W.template residual<OPEN>(H - 1, par0, diag0, invw0);
+    if constexpr (OPEN) {
+        const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
+        const long st = (long)TILE_WARPS * L.stride();
+#pragma unroll
+        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
+            int a = H + warp + r * TILE_WARPS;
+            if (a >= WJ - H) break;
+            int rp = (par0 + a) & 1;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int b = 2 * k + h;
+                if (b < H || b >= TW - H) continue;
+                xout[g0 + r * st + h] = (TX)W.X[W.at(rp ^ h, a, k)];
+            }
+        }
+    } else {
         const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
         for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
@@ -350,7 +455,7 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
         int cj = t / (TI / 2), ci = t - cj * (TI / 2);
         int J = tj0 / 2 + cj, I = ti0 / 2 + ci;            // aggregate of fine rows 2J, 2J+1
         int Jc = J + L.pj_off();                           // its row in the coarse array
-        if (Jc >= nyc || I >= nxc) continue;
+        if (Jc >= A.nyc || I >= A.nxc) continue;
         const int a0 = 2 * cj + H, b0 = 2 * ci + H;        // = 2J - wj0, 2I - wi0
         const int kA = (b0 - 1) >> 1, kB = b0 >> 1, kC = (b0 + 1) >> 1, kD = (b0 + 2) >> 1;
         int cA = (par0 + a0 - 1 + b0 - 1) & 1;             // colour of (a0-1, b0-1)
@@ -365,50 +470,65 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
             row += TK;
             cA ^= 1;
         }
-        bc[(long)(Jc + 1) * pitchc + I + 1] = (TC)acc;
+        bc[(long)(Jc + 1) * A.pitchc + I + 1] = (TC)acc;
     }
 }
 
-// ---------------------------------------------------------------------------
-// UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
-// ---------------------------------------------------------------------------
-template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
 __global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
-k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
-        const double *__restrict__ scal, int sumr_slot, double inv_n,
-        int nyc, int nxc, int pitchc, int periodic_c, const TC *__restrict__ xc,
-        double *part, unsigned int *count, double *out) {
-    constexpr int H = halo_up(NU);
+k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
+          const double *__restrict__ scal, int sumr_slot, double inv_n, DownArgs A, TC *__restrict__ bc) {
+    constexpr int H = halo_down(NU, ZERO);
     constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
-    constexpr int CJ = WJ / 2 + 3, CI = TW / 2 + 3;
     extern __shared__ __align__(16) unsigned char smem[];
     Window<T, FINE, WJ> W;
     W.carve(smem);
-    TC *XC = reinterpret_cast<TC *>(smem + ((Window<T, FINE, WJ>::bytes() + 15) & ~size_t(15)));
     const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
-    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     double fshift = 0.0;
     if constexpr (FINE) {
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
         W.fill_tables(&L.F, L.dirichlet());
         if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
     } else W.fill_tables(nullptr, L.dirichlet());
-    // ---- coarse window
-    const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
-    for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
-        int a = t / CI, b = t - a * CI;
-        int J = cj0 + a + L.pj_off(), I = ci0 + b;
-        TC v = TC(0);
-        if (J >= 0 && J < nyc) {
-            if (periodic_c) I = wrap_col(I, nxc);
-            if (I >= 0 && I < nxc) v = xc[(long)(J + 1) * pitchc + I + 1];
+    if constexpr (FINE) {
+        int open = 0;
+        if (A.allow_open && L.inside(wj0, wi0, WJ, TW))      // block-uniform
+            open = W.template load_inside<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        else
+            W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        if (__syncthreads_and(open)) {
+            down_body<true, T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
+            return;
         }
-        XC[t] = v;
+    } else {
+        W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        __syncthreads();
     }
-    W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-    __syncthreads();
+    down_body<false, T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
+}
+
+// ---------------------------------------------------------------------------
+// UP leg.   x <- x + P xc ;  NU sweeps (B,R) ;  [DOT: out = (sum f x, sum x)]
+// ---------------------------------------------------------------------------
+struct UpArgs {
+    int nyc, nxc, pitchc, periodic_c;
+    int allow_open;
+};
+
+template <bool OPEN, typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+__device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, const TC *XC, TX *__restrict__ xout,
+                                        const TF *__restrict__ fin, double fscale, double fshift, int tj0, int ti0,
+                                        double (&acc)[2]) {
+    constexpr int H = halo_up(NU);
+    constexpr int CI = TW / 2 + 3;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+    const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
+    T dinv0 = T(0), invw0 = T(0);
+    if constexpr (OPEN) { dinv0 = W.tab_dinv[31]; invw0 = W.tab_invw[7]; }
     // ---- prolongation on the whole window
 #pragma unroll
     for (int r = 0; r < WJ / TILE_WARPS; r++) {
@@ -418,24 +538,49 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int b = 2 * k + h, p = W.at(rp ^ h, a, k);
-            uint8_t bits = W.B[p];
-            if (!(bits & NB_SELF)) continue;
+            T w = invw0;
+            if constexpr (!OPEN) {
+                uint8_t bits = W.B[p];
+                if (!(bits & NB_SELF)) continue;
+                w = W.tab_invw[bits >> 5];
+            }
             int i = wi0 + b;
             int I0 = (i >> 1) - ci0, In = I0 + ((i & 1) ? 1 : -1);
-            T v = T(9) * (T)XC[J0 * CI + I0] + T(3) * ((T)XC[Jn * CI + I0] + (T)XC[J0 * CI + In]) + (T)XC[Jn * CI + In];
-            W.X[p] += v * W.tab_invw[bits >> 5];
+            T v = prol_val((T)XC[J0 * CI + I0], (T)XC[Jn * CI + I0], (T)XC[J0 * CI + In], (T)XC[Jn * CI + In]);
+            W.X[p] = mul_add(v, w, W.X[p]);
         }
     }
     __syncthreads();
     // ---- NU sweeps, black then red
 #pragma unroll
     for (int hs = 0; hs < 2 * NU; hs++) {
-        W.template relax<false>(1 - (hs & 1), hs + 1, par0);
+        W.template relax<false, OPEN>(1 - (hs & 1), hs + 1, par0, dinv0);
         __syncthreads();
     }
     // ---- write the interior (+ dots)
-    double acc[2] = {0.0, 0.0};
-    {
+    if constexpr (OPEN) {
+        const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
+        const long st = (long)TILE_WARPS * L.stride();
+#pragma unroll
+        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
+            int a = H + warp + r * TILE_WARPS;
+            if (a >= WJ - H) break;
+            int rp = (par0 + a) & 1;
+            const bool own = L.owned(wj0 + a);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int b = 2 * k + h;
+                if (b < H || b >= TW - H) continue;
+                const long g = g0 + r * st + h;
+                T xv = W.X[W.at(rp ^ h, a, k)];
+                xout[g] = (TX)xv;
+                if (DOT && own) {
+                    double fv = __fma_rn(fscale, (double)fin[g], -fshift);
+                    acc[0] = __fma_rn(fv, (double)xv, acc[0]); acc[1] += (double)xv;
+                }
+            }
+        }
+    } else {
         const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
         for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
@@ -454,12 +599,73 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
                 xout[rb + ch] = (TX)xv;
                 if (DOT && L.owned(j)) {
                     // the dot uses the fp64 residual, not its narrowed copy in shared memory
-                    double fv = fscale * (double)fin[rb + ch] - fshift;
-                    acc[0] += fv * (double)xv; acc[1] += (double)xv;
+                    double fv = __fma_rn(fscale, (double)fin[rb + ch], -fshift);
+                    acc[0] = __fma_rn(fv, (double)xv, acc[0]); acc[1] += (double)xv;
                 }
             }
         }
     }
+}
+
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
+k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
+        const double *__restrict__ scal, int sumr_slot, double inv_n, UpArgs A, const TC *__restrict__ xc,
+        double *part, unsigned int *count, double *out) {
+    constexpr int H = halo_up(NU);
+    constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
+    constexpr int CJ = WJ / 2 + 3, CI = TW / 2 + 3;
+    extern __shared__ __align__(16) unsigned char smem[];
+    Window<T, FINE, WJ> W;
+    W.carve(smem);
+    TC *XC = reinterpret_cast<TC *>(smem + ((Window<T, FINE, WJ>::bytes() + 15) & ~size_t(15)));
+    const int tj0 = blockIdx.y * TJ, ti0 = blockIdx.x * TI;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    double fshift = 0.0;
+    if constexpr (FINE) {
+        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+        W.fill_tables(&L.F, L.dirichlet());
+        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
+    } else W.fill_tables(nullptr, L.dirichlet());
+    // ---- coarse window
+    const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
+    const int Jc0 = cj0 + L.pj_off();
+    if (Jc0 >= 0 && Jc0 + CJ <= A.nyc && ci0 >= 0 && ci0 + CI <= A.nxc) {   // block-uniform: no bounds, no wrap
+        const TC *src = xc + (long)(Jc0 + 1) * A.pitchc + ci0 + 1;
+        for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
+            int a = t / CI, b = t - a * CI;
+            XC[t] = src[a * A.pitchc + b];
+        }
+    } else {
+        for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
+            int a = t / CI, b = t - a * CI;
+            int J = Jc0 + a, I = ci0 + b;
+            TC v = TC(0);
+            if (J >= 0 && J < A.nyc) {
+                if (A.periodic_c) I = wrap_col(I, A.nxc);
+                if (I >= 0 && I < A.nxc) v = xc[(long)(J + 1) * A.pitchc + I + 1];
+            }
+            XC[t] = v;
+        }
+    }
+    double acc[2] = {0.0, 0.0};
+    bool done = false;
+    if constexpr (FINE) {
+        int open = 0;
+        if (A.allow_open && L.inside(wj0, wi0, WJ, TW))      // block-uniform
+            open = W.template load_inside<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        else
+            W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        if (__syncthreads_and(open)) {
+            up_body<true, T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
+            done = true;
+        }
+    } else {
+        W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
+        __syncthreads();
+    }
+    if (!done) up_body<false, T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
     if (DOT) grid_reduce<OpSum, 2>(acc, part, count, out);
 }
 

@@ -243,3 +243,53 @@ def test_large_grid_solves_converge_and_fused_matches_unfused(xper):
         e.close()
     for loc in ("c", "v", "h"):
         assert abs(its[(0, loc)] - its[(2, loc)]) <= 2, its
+
+
+_OPEN_TILE_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {root!r} + "/tests")
+from util import plain_param
+from fluids2d_b200._cabi import Engine
+rng = np.random.default_rng(11)
+out = {{}}
+for xper in (False, True):
+    e = Engine(plain_param(model="rsw", nx=768, ny=512, Lx=3.0, Ly=2.0, xperiodic=xper), solver_rtol=1e-12)
+    e.set_mask(None)
+    msk = e.mesh_array("msk")
+    yy, xx = np.mgrid[0:msk.shape[0], 0:msk.shape[1]]
+    msk[(xx - 500) ** 2 + (yy - 300) ** 2 < 40 * 40] = 0
+    e.set_mask(msk)
+    for loc in ("c", "v", "h"):
+        m = (e.mesh_array("msk") if loc == "c" else e.mesh_array("mskv")).astype(bool)
+        if xper:
+            m[:, :3] = False
+            m[:, -3:] = False
+        b = rng.standard_normal(e.shape) * m
+        if loc == "c":
+            b[m] -= b[m].mean()
+        x = np.zeros(e.shape)
+        it, rr = e.solve(loc, b, x)
+        out[f"{{int(xper)}}{{loc}}"] = x
+        out[f"{{int(xper)}}{{loc}}_it"] = np.array([it])
+    e.close()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_open_tile_path_gives_the_same_bits_as_the_masked_path(tmp_path):
+    """mg_tiles.cuh: tiles whose window is all fluid take a path without mask
+    look-ups and bounds tests.  With F2D_NO_OPEN=1 every tile takes the generic
+    path; the solutions (islands, closed and x-periodic, centres / vertices /
+    Helmholtz) must be bit-identical and need the same iterations."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("open", {}), ("generic", {"F2D_NO_OPEN": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", _OPEN_TILE_SNIPPET.format(root=root), path], check=True,
+                       env={**os.environ, **env}, timeout=600)
+        res[tag] = np.load(path)
+    for k in res["open"].files:
+        assert np.array_equal(res["open"][k], res["generic"][k]), k
