@@ -81,6 +81,9 @@ __device__ __forceinline__ double fine_offdiag(const Stencil &s, uint8_t c, cons
     return a;
 }
 
+// shared-memory arrays per level of the single-CTA tail kernel: x, b, r, cx, cy, dinv, w
+constexpr int TAIL_ARRAYS = 7;
+
 // normaliser of the prolongation weights.  Neumann: renormalise over the fluid
 // parents (constants are interpolated exactly next to walls).  Dirichlet: a
 // masked parent IS the wall value 0, so the plain bilinear weights stand.
@@ -810,10 +813,10 @@ int mg_build(f2d_ctx *c, int which) {
     M.tail = (int)M.lev.size() - 1;
     for (int l = (int)M.lev.size() - 1; l >= 1; l--)
         if ((long)M.lev[l].ny * M.lev[l].nx <= 4096 && (int)M.lev.size() - l <= 16) M.tail = l;
-    {   // x, b, r of every tail level must fit in shared memory
+    {   // x, b, r and the coefficient copies of every tail level must fit in shared memory
         auto need = [&](int from) {
             size_t b = 0;
-            for (size_t l = from; l < M.lev.size(); l++) b += (size_t)3 * (M.lev[l].ny + 2) * (M.lev[l].nx + 2) * sizeof(CT);
+            for (size_t l = from; l < M.lev.size(); l++) b += (size_t)TAIL_ARRAYS * (M.lev[l].ny + 2) * (M.lev[l].nx + 2) * sizeof(CT);
             return b;
         };
         while (M.tail < (int)M.lev.size() - 1 && need(M.tail) > 200 * 1024) M.tail++;
@@ -1043,13 +1046,15 @@ static int mg_build_slab(f2d_ctx *c, int which) {
 
 // ---------------------------------------------------------------------------
 // single-CTA tail: the whole sub-V-cycle of the levels whose grids are small
-// (<= 4096 points) in one launch.  x, b and the residual of every tail level
-// live in shared memory (the only arrays with write -> read dependencies inside
-// the kernel); the coefficients are read through the read-only path.
+// (<= 4096 points) in one launch.  Everything lives in shared memory: x, b and
+// the residual of every tail level, and a copy of the coefficients (couplings,
+// inverse diagonal, prolongation normaliser) made once at the start with all
+// loads in flight -- the kernel is a chain of ~80 short phases separated by
+// barriers, and a global (L2) load in each of them was most of its run time.
 // ---------------------------------------------------------------------------
 struct TailLevel {
     int ny, nx, pitch;          // global arrays: (ny+2) x pitch
-    int sp, off;                // shared arrays: pitch nx+2, offset (in CT) of x; b, r follow
+    int sp, off;                // shared arrays: pitch nx+2, offset (in CT) of x; b, r, cx, cy, dinv, w follow
     CT *x;
     const CT *b;
     const CT *cx, *cy, *dinv;
@@ -1064,21 +1069,20 @@ struct TailArgs {
     for (int J = threadIdx.x >> 5; J < (L).ny; J += 32)         \
         for (int I = threadIdx.x & 31; I < (L).nx; I += 32)
 
-struct TailSm { CT *x, *b, *r; };
+struct TailSm { CT *x, *b, *r, *cx, *cy, *dinv, *w; };
 __device__ __forceinline__ TailSm tail_sm(CT *sm, const TailLevel &L) {
     int n = (L.ny + 2) * L.sp;
-    return TailSm{sm + L.off, sm + L.off + n, sm + L.off + 2 * n};
+    CT *p = sm + L.off;
+    return TailSm{p, p + n, p + 2 * n, p + 3 * n, p + 4 * n, p + 5 * n, p + 6 * n};
 }
 
-__device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const CT *x, int periodic, int J, int I) {
-    long g = (long)(J + 1) * L.pitch + I + 1, ge = g + 1;
+__device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const TailSm &S, int periodic, int J, int I) {
     int s = (J + 1) * L.sp + I + 1, w = s - 1, e = s + 1;
     if (periodic) {
         if (I == 0) w = s + (L.nx - 1);
-        if (I == L.nx - 1) { e = s - (L.nx - 1); ge = g - (L.nx - 1); }
+        if (I == L.nx - 1) e = s - (L.nx - 1);
     }
-    return __ldg(L.cx + g) * x[w] + __ldg(L.cx + ge) * x[e] + __ldg(L.cy + g) * x[s - L.sp] +
-           __ldg(L.cy + g + L.pitch) * x[s + L.sp];
+    return S.cx[s] * S.x[w] + S.cx[e] * S.x[e] + S.cy[s] * S.x[s - L.sp] + S.cy[s + L.sp] * S.x[s + L.sp];
 }
 
 __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
@@ -1086,9 +1090,9 @@ __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int perio
     // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
     for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
         for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) {
-            CT di = __ldg(L.dinv + (long)(J + 1) * L.pitch + I + 1);
             int s = (J + 1) * L.sp + I + 1;
-            CT a = zero ? CT(0) : tail_offdiag(L, S.x, periodic, J, I);
+            CT di = S.dinv[s];
+            CT a = zero ? CT(0) : tail_offdiag(L, S, periodic, J, I);
             S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
         }
     __syncthreads();
@@ -1104,11 +1108,24 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
     __syncthreads();
     CT *sm = reinterpret_cast<CT *>(smem_raw);
     const int per = A.periodic;
-    {   // right-hand side of the first tail level comes from the level above
-        const TailLevel &L = A.lev[0];
+    // coefficients of every tail level (halo rows / columns included: the east and
+    // north faces of the last column / row live there), and the right-hand side
+    // of the first tail level, which comes from the level above
+    for (int l = 0; l < A.nlev; l++) {
+        const TailLevel &L = A.lev[l];
         TailSm S = tail_sm(sm, L);
-        TAIL_LOOP(L) S.b[(J + 1) * L.sp + I + 1] = L.b[(long)(J + 1) * L.pitch + I + 1];
+        const int n = (L.ny + 2) * L.sp;
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            int j = t / L.sp, i = t - j * L.sp;
+            long g = (long)j * L.pitch + i;
+            S.cx[t] = __ldg(L.cx + g);
+            S.cy[t] = __ldg(L.cy + g);
+            S.dinv[t] = __ldg(L.dinv + g);
+            S.w[t] = (CT)w16_of(__ldg(L.code + g), A.dirichlet);
+            if (l == 0) S.b[t] = __ldg(L.b + g);
+        }
     }
+    __syncthreads();
     for (int l = 0; l < A.nlev - 1; l++) {
         const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
         TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
@@ -1119,12 +1136,11 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
             tail_relax(L, sm, per, 1, false);
         }
         TAIL_LOOP(L) {   // residual / prolongation normaliser
-            long g = (long)(J + 1) * L.pitch + I + 1;
             int sidx = (J + 1) * L.sp + I + 1;
-            CT di = __ldg(L.dinv + g), res = CT(0);
+            CT di = S.dinv[sidx], res = CT(0);
             if (di != CT(0)) {
-                CT a = tail_offdiag(L, S.x, per, J, I);
-                res = (S.b[sidx] - (S.x[sidx] / di - a)) / (CT)w16_of(__ldg(L.code + g), A.dirichlet);
+                CT a = tail_offdiag(L, S, per, J, I);
+                res = (S.b[sidx] - (S.x[sidx] / di - a)) / S.w[sidx];
             }
             S.r[sidx] = res;
         }
@@ -1161,14 +1177,14 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
         const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
         TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
         TAIL_LOOP(L) {
-            uint8_t c = __ldg(L.code + (long)(J + 1) * L.pitch + I + 1);
-            if (!(c & NB_SELF)) continue;
+            int sidx = (J + 1) * L.sp + I + 1;
+            if (S.dinv[sidx] == CT(0)) continue;      // not an unknown (set-up clears the code where 1/diag is 0)
             int J0, Jn, I0, In;
             parents(J, I, J0, Jn, I0, In);
             if (per) In = wrap_mod(In, C.nx);
             int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
             CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
-            S.x[(J + 1) * L.sp + I + 1] += v / (CT)w16_of(c, A.dirichlet);
+            S.x[sidx] += v / S.w[sidx];
         }
         __syncthreads();
         for (int s = 0; s < A.nu2; s++) {
@@ -1317,7 +1333,7 @@ static int launch_tail(f2d_ctx *c, Multigrid &M) {
         const Level &L = TL[l];
         int sp = L.nx + 2;
         A.lev[l - first] = TailLevel{L.ny, L.nx, L.pitch, sp, off, L.x, L.b, L.cx, L.cy, L.dinv, L.code};
-        off += 3 * (L.ny + 2) * sp;
+        off += TAIL_ARRAYS * (L.ny + 2) * sp;
     }
     if (slab) {   // right-hand side: every rank's owned rows of level `tail`
         const Level &LT = M.lev[M.tail];

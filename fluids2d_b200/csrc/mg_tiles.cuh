@@ -84,6 +84,16 @@ __device__ __forceinline__ double prol_val(double x00, double xn0, double x0n, d
 __device__ __forceinline__ float mul_add(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double mul_add(double a, double b, double c) { return __fma_rn(a, b, c); }
 
+// global -> shared without a register in between (LDGSTS): the copy is in flight
+// while the thread goes on, which keeps the window fetch inside the register budget
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async sizes");
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ int wrap_mod(int i, int n) {
     i %= n;
     return i < 0 ? i + n : i;
@@ -203,10 +213,8 @@ struct Window {
     // A warp owns rows a0, a0+16, ... which all have the parity of a0, so the
     // column offset o, the bounds test and every neighbour offset are hoisted;
     // the unrolled body is loads at constant offsets from one base pointer.
-    // OPEN (FINE only): every point of the window is an unknown with four open
-    // faces -> constant inverse diagonal dinv0, no mask look-up.
-    template <bool NO_NEIGHBOURS, bool OPEN>
-    __device__ __forceinline__ void relax(int col, int m, int par0, T dinv0) {
+    template <bool NO_NEIGHBOURS>
+    __device__ __forceinline__ void relax(int col, int m, int par0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
         const int a0 = m + warp;
         const int o = col ^ ((par0 + a0) & 1), b = 2 * k + o;
@@ -226,14 +234,13 @@ struct Window {
                 if constexpr (FINE) off = nb_sum(cxf, cyf, xw, xe, xs, xn);
                 else off = CX[p0 + r * S] * xw + CX[q0 + o + r * S] * xe + CY[p0 + r * S] * xs + CY[q0 + TK + r * S] * xn;
             }
-            if constexpr (FINE) xp[r * S] = gs_new(fp[r * S], off, OPEN ? dinv0 : tab_dinv[B[p0 + r * S] & 31]);
+            if constexpr (FINE) xp[r * S] = gs_new(fp[r * S], off, tab_dinv[B[p0 + r * S] & 31]);
             else xp[r * S] = (fp[r * S] + off) * DI[p0 + r * S];
         }
     }
 
     // residual, pre-multiplied by 1/normaliser of the prolongation, into Fv (ring m)
-    template <bool OPEN>
-    __device__ __forceinline__ void residual(int m, int par0, T diag0, T invw0) {
+    __device__ __forceinline__ void residual(int m, int par0) {
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
         const int a0 = m + warp;
         const int rp = (par0 + a0) & 1;
@@ -250,30 +257,19 @@ struct Window {
                 const int p = p0 + r * S;
                 const T *q = X + q0 + r * S;
                 T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
-                T res;
-                if constexpr (FINE && OPEN) {
-                    res = res_val(Fv[p], diag0, X[p], nb_sum(cxf, cyf, xw, xe, xs, xn), invw0);
+                uint8_t bits = B[p];
+                T off, diag;
+                if constexpr (FINE) {
+                    off = nb_sum(cxf, cyf, xw, xe, xs, xn);
+                    diag = tab_diag[bits & 31];
                 } else {
-                    uint8_t bits = B[p];
-                    T off, diag;
-                    if constexpr (FINE) {
-                        off = nb_sum(cxf, cyf, xw, xe, xs, xn);
-                        diag = tab_diag[bits & 31];
-                    } else {
-                        off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
-                        T di = DI[p];
-                        diag = di != T(0) ? T(1) / di : T(0);
-                    }
-                    res = (bits & NB_SELF) ? res_val(Fv[p], diag, X[p], off, tab_invw[bits >> 5]) : T(0);
+                    off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
+                    T di = DI[p];
+                    diag = di != T(0) ? T(1) / di : T(0);
                 }
-                Fv[p] = res;    // each thread only overwrites what it alone reads
+                Fv[p] = (bits & NB_SELF) ? res_val(Fv[p], diag, X[p], off, tab_invw[bits >> 5]) : T(0);
             }
         }
-    }
-
-    __device__ __forceinline__ T &Fat(int par0, int a, int b) {
-        int c = (par0 + a + b) & 1;
-        return Fv[at(c, a, b >> 1)];
     }
 
     // global -> shared: every load of a thread is issued before its first use
@@ -335,22 +331,27 @@ struct Window {
         }
     }
 
-    // FINE, window wholly inside the array (Lev::inside): the same load without
-    // bounds tests or wraps.  Fills the window exactly as load() does and returns
-    // whether every mask byte this thread saw is 0xFF.
+    // ---- open tiles (FINE): fixed ownership, f and x in registers -------------
+    // Thread (warp w, lane k) owns rows w, w+16, ... x columns 2k, 2k+1 for the
+    // whole leg.  Its rows share one parity rp, so its colour-c points sit in
+    // column 2k + (c ^ rp); registers are indexed [row][colour].  Of the four
+    // neighbours of a point one is the thread's own point of the other colour
+    // (a register), one belongs to the next lane and two to the next warps: three
+    // shared-memory loads instead of five, none for f, no mask byte, no table.
+    static constexpr int RO = WJ / TILE_WARPS;
+
+    // the window without bounds tests or wraps (Lev::inside): global -> registers.
+    // Only issues the loads; the caller does its set-up work before it looks at them.
     template <bool LOAD_X, class Lev, typename TX, typename TF>
-    __device__ __forceinline__ bool load_inside(const Lev &L, const TX *__restrict__ xin, const TF *__restrict__ fin,
-                                                double fscale, double fshift, int wj0, int wi0, int par0) {
+    __device__ __forceinline__ void fetch_inside(const Lev &L, const TX *__restrict__ xin, const TF *__restrict__ fin,
+                                                 int wj0, int wi0, TF (&fv)[RO][2], TX (&xv)[RO][2],
+                                                 uint8_t (&bits)[RO][2]) {
         static_assert(FINE, "open tiles exist on the fine level only");
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-        constexpr int R = WJ / TILE_WARPS;
         const long g0 = L.base(wj0 + warp, wi0 + 2 * k);
         const long st = (long)TILE_WARPS * L.stride();
-        TF fv[R][2];
-        TX xv[R][2];
-        uint8_t bits[R][2];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
+        for (int r = 0; r < RO; r++) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const long g = g0 + r * st + h;
@@ -360,21 +361,127 @@ struct Window {
                 if (LOAD_X) xv[r][h] = xin[g];
             }
         }
+    }
+    // x of the thread's points: global -> X directly (cp.async), no registers
+    template <class Lev, typename TX>
+    __device__ __forceinline__ void fetch_x_async(const Lev &L, const TX *__restrict__ xin, int wj0, int wi0, int par0) {
+        static_assert(sizeof(TX) == sizeof(T), "x is stored in the type it is relaxed in");
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const TX *src = xin + L.base(wj0 + warp, wi0 + 2 * k);
+        const long st = (long)TILE_WARPS * L.stride();
+        const int rp = (par0 + warp) & 1;
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
+            cp_async<sizeof(T)>(X + at(rp, warp + r * TILE_WARPS, k), src + r * st);
+            cp_async<sizeof(T)>(X + at(rp ^ 1, warp + r * TILE_WARPS, k), src + r * st + 1);
+        }
+    }
+    // every mask byte this thread fetched is 0xFF
+    __device__ __forceinline__ static bool all_open(const uint8_t (&bits)[RO][2]) {
         unsigned all = 0xFFu;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
+        for (int r = 0; r < RO; r++) all &= bits[r][0] & bits[r][1];
+        return all == 0xFFu;
+    }
+
+    // registers -> shared memory, exactly what load() leaves (an inside tile that is not open)
+    // X_ASYNC: x already sits in X (fetch_x_async): only clear the masked entries
+    template <bool X_ASYNC, typename TX, typename TF>
+    __device__ __forceinline__ void stash(const TF (&fv)[RO][2], const TX (&xv)[RO][2], const uint8_t (&bits)[RO][2],
+                                          double fscale, double fshift, int par0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
             int a = warp + r * TILE_WARPS, rp = (par0 + a) & 1;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 int p = at(rp ^ h, a, k);
                 bool self = bits[r][h] & NB_SELF;
-                all &= bits[r][h];
                 B[p] = bits[r][h];
                 Fv[p] = self ? (T)__fma_rn(fscale, (double)fv[r][h], -fshift) : T(0);
-                X[p] = self ? (T)xv[r][h] : T(0);
+                if (!X_ASYNC) X[p] = self ? (T)xv[r][h] : T(0);
+                else if (!self) X[p] = T(0);
             }
         }
-        return all == 0xFFu;
+    }
+
+    // [row][column] -> [row][colour] registers (+ scale/shift/narrow of f)
+    // X_ASYNC: x comes from X, where fetch_x_async put it (already by colour)
+    template <bool X_ASYNC, typename TX, typename TF>
+    __device__ __forceinline__ void own(const TF (&fv)[RO][2], const TX (&xv)[RO][2], double fscale, double fshift,
+                                        int rp, T (&fr)[RO][2], T (&xr)[RO][2]) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
+            T f0 = (T)__fma_rn(fscale, (double)fv[r][0], -fshift), f1 = (T)__fma_rn(fscale, (double)fv[r][1], -fshift);
+            fr[r][0] = rp ? f1 : f0; fr[r][1] = rp ? f0 : f1;
+            if (X_ASYNC) {
+                xr[r][0] = X[at(0, warp + r * TILE_WARPS, k)];
+                xr[r][1] = X[at(1, warp + r * TILE_WARPS, k)];
+            } else {
+                T x0 = (T)xv[r][0], x1 = (T)xv[r][1];
+                xr[r][0] = rp ? x1 : x0; xr[r][1] = rp ? x0 : x1;
+            }
+        }
+    }
+
+    // xr -> X (both colours, whole window)
+    __device__ __forceinline__ void publish(const T (&xr)[RO][2]) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
+            X[at(0, warp + r * TILE_WARPS, k)] = xr[r][0];
+            X[at(1, warp + r * TILE_WARPS, k)] = xr[r][1];
+        }
+    }
+
+    // half-sweep of colour c (a constant once the caller's loop is unrolled) on ring m
+    template <bool NO_NEIGHBOURS>
+    __device__ __forceinline__ void relax_open(int c, int m, int rp, const T (&fr)[RO][2], T (&xr)[RO][2], T dinv0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const int o = c ^ rp, b = 2 * k + o;
+        if (b < m || b >= TW - m) return;
+        constexpr int S = TILE_WARPS * TK;
+        T *xp = X + at(c, warp, k);
+        const T *xq = X + at(1 - c, warp, k);
+        const int side = 2 * o - 1;     // the W (o = 0) or E (o = 1) neighbour is another lane's point
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
+            const int a = warp + r * TILE_WARPS;
+            if (a < m || a >= WJ - m) continue;
+            T off = T(0);
+            if (!NO_NEIGHBOURS) {
+                const T *q = xq + r * S;
+                T xl = q[side], xs = q[-TK], xn = q[TK], mine = xr[r][1 - c];
+                off = nb_sum(cxf, cyf, mine, xl, xs, xn);     // xw + xe commutes: no need to know which is which
+            }
+            T v = gs_new(fr[r][c], off, dinv0);
+            xr[r][c] = v;
+            xp[r * S] = v;
+        }
+    }
+
+    // residual (x 1/16) of both colours on ring m into Fv
+    __device__ __forceinline__ void residual_open(int m, int rp, const T (&fr)[RO][2], const T (&xr)[RO][2], T diag0,
+                                                  T invw0) {
+        const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        constexpr int S = TILE_WARPS * TK;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int o = c ^ rp, b = 2 * k + o;
+            if (b < m || b >= TW - m) continue;
+            const T *xq = X + at(1 - c, warp, k);
+            T *fp = Fv + at(c, warp, k);
+            const int side = 2 * o - 1;
+#pragma unroll
+            for (int r = 0; r < RO; r++) {
+                const int a = warp + r * TILE_WARPS;
+                if (a < m || a >= WJ - m) continue;
+                const T *q = xq + r * S;
+                T xl = q[side], xs = q[-TK], xn = q[TK], mine = xr[r][1 - c];
+                fp[r * S] = res_val(fr[r][c], diag0, xr[r][c], nb_sum(cxf, cyf, mine, xl, xs, xn), invw0);
+            }
+        }
     }
 };
 
@@ -392,42 +499,61 @@ struct DownArgs {
     int allow_open;         // 0: every tile takes the generic path (F2D_NO_OPEN, A/B tests)
 };
 
-// everything after the window is loaded; OPEN: see the header comment
-template <bool OPEN, typename T, typename TX, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
+// restriction R = P^T of the residual in W.Fv: weights (1,3,3,1) x (1,3,3,1) over
+// the 4 x 4 fine cells around the aggregate.  In the colour-separated layout the
+// four columns of a row are (cA,kA) (cB,kB) (cA,kC) (cB,kD) with cB = 1 - cA, and
+// cA flips from one row to the next: four loads at fixed offsets per row.  A warp
+// takes one coarse row at a time (lane = coarse column): consecutive lanes read
+// consecutive words, no bank conflicts and no division.
+template <typename T, typename TC, bool FINE, int WJ, int H, class Lev>
+__device__ __forceinline__ void restrict_tile(const Window<T, FINE, WJ> &W, const Lev &L, const DownArgs &A,
+                                              TC *__restrict__ bc, int tj0, int ti0, int par0) {
+    constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
+    static_assert(TI / 2 <= 32, "one lane per coarse column");
+    const int warp = threadIdx.x >> 5, ci = threadIdx.x & 31;
+    if (ci >= TI / 2) return;
+    const int I = ti0 / 2 + ci;
+    if (I >= A.nxc) return;
+    const int b0 = 2 * ci + H;                             // = 2I - wi0
+    const int kA = (b0 - 1) >> 1, kB = b0 >> 1, kC = (b0 + 1) >> 1, kD = (b0 + 2) >> 1;
+    constexpr int PL = WJ * TK;                            // one colour plane
+    for (int cj = warp; cj < TJ / 2; cj += TILE_WARPS) {
+        int Jc = tj0 / 2 + cj + L.pj_off();                // aggregate of fine rows 2J, 2J+1: its row in the coarse array
+        if (Jc >= A.nyc) break;
+        const int a0 = 2 * cj + H;                         // = 2J - wj0
+        int cA = (par0 + a0 - 1 + b0 - 1) & 1;             // colour of (a0-1, b0-1)
+        const T *row = W.Fv + (a0 - 1) * TK;
+        T acc = T(0);
+#pragma unroll
+        for (int da = 0; da < 4; da++) {
+            const T *pa = row + cA * PL, *pb = row + (1 - cA) * PL;
+            T v = (pa[kA] + pb[kD]) + T(3) * (pb[kB] + pa[kC]);
+            acc += (da == 1 || da == 2) ? T(3) * v : v;
+            row += TK;
+            cA ^= 1;
+        }
+        bc[(long)(Jc + 1) * A.pitchc + I + 1] = (TC)acc;
+    }
+}
+
+// generic path: everything after the window is loaded
+template <typename T, typename TX, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
 __device__ __forceinline__ void down_body(Window<T, FINE, WJ> &W, const Lev &L, TX *__restrict__ xout,
                                           const DownArgs &A, TC *__restrict__ bc, int tj0, int ti0) {
     constexpr int H = halo_down(NU, ZERO);
-    constexpr int TJ = WJ - 2 * H, TI = TW - 2 * H;
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-    T dinv0 = T(0), diag0 = T(0), invw0 = T(0);
-    if constexpr (OPEN) { dinv0 = W.tab_dinv[31]; diag0 = W.tab_diag[31]; invw0 = W.tab_invw[7]; }
     // ---- NU sweeps, red then black
 #pragma unroll
     for (int hs = 0; hs < 2 * NU; hs++) {
-        if (ZERO && hs == 0) W.template relax<true, OPEN>(0, 0, par0, dinv0);
-        else W.template relax<false, OPEN>(hs & 1, ZERO ? hs : hs + 1, par0, dinv0);
+        if (ZERO && hs == 0) W.template relax<true>(0, 0, par0);
+        else W.template relax<false>(hs & 1, ZERO ? hs : hs + 1, par0);
         __syncthreads();
     }
     // ---- residual on the tile +- 1, then write x and the restricted residual
-    W.template residual<OPEN>(H - 1, par0, diag0, invw0);
-    if constexpr (OPEN) {
-        const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
-        const long st = (long)TILE_WARPS * L.stride();
-#pragma unroll
-        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
-            int a = H + warp + r * TILE_WARPS;
-            if (a >= WJ - H) break;
-            int rp = (par0 + a) & 1;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int b = 2 * k + h;
-                if (b < H || b >= TW - H) continue;
-                xout[g0 + r * st + h] = (TX)W.X[W.at(rp ^ h, a, k)];
-            }
-        }
-    } else {
+    W.residual(H - 1, par0);
+    {
         const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
         for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
@@ -447,31 +573,45 @@ __device__ __forceinline__ void down_body(Window<T, FINE, WJ> &W, const Lev &L, 
         }
     }
     __syncthreads();
-    // restriction R = P^T: weights (1,3,3,1) x (1,3,3,1) over the 4 x 4 fine cells
-    // around the aggregate.  In the colour-separated layout the four columns of
-    // a row are (cA,kA) (cB,kB) (cA,kC) (cB,kD) with cB = 1 - cA, and cA flips
-    // from one row to the next: four loads at fixed offsets per row.
-    for (int t = threadIdx.x; t < (TJ / 2) * (TI / 2); t += TILE_THREADS) {
-        int cj = t / (TI / 2), ci = t - cj * (TI / 2);
-        int J = tj0 / 2 + cj, I = ti0 / 2 + ci;            // aggregate of fine rows 2J, 2J+1
-        int Jc = J + L.pj_off();                           // its row in the coarse array
-        if (Jc >= A.nyc || I >= A.nxc) continue;
-        const int a0 = 2 * cj + H, b0 = 2 * ci + H;        // = 2J - wj0, 2I - wi0
-        const int kA = (b0 - 1) >> 1, kB = b0 >> 1, kC = (b0 + 1) >> 1, kD = (b0 + 2) >> 1;
-        int cA = (par0 + a0 - 1 + b0 - 1) & 1;             // colour of (a0-1, b0-1)
-        constexpr int PL = WJ * TK;                        // one colour plane
-        const T *row = W.Fv + (a0 - 1) * TK;
-        T acc = T(0);
+    restrict_tile<T, TC, FINE, WJ, H>(W, L, A, bc, tj0, ti0, par0);
+}
+
+// open tile: registers fr / xr hold the thread's 2 x RO points
+template <typename T, typename TX, typename TC, bool ZERO, int NU, int WJ, class Lev>
+__device__ __forceinline__ void down_open(Window<T, true, WJ> &W, const Lev &L, TX *__restrict__ xout,
+                                          const DownArgs &A, TC *__restrict__ bc, int tj0, int ti0,
+                                          const T (&fr)[WJ / TILE_WARPS][2], T (&xr)[WJ / TILE_WARPS][2]) {
+    constexpr int H = halo_down(NU, ZERO), RO = WJ / TILE_WARPS;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+    const int rp = (par0 + warp) & 1;
+    const T dinv0 = W.tab_dinv[31], diag0 = W.tab_diag[31], invw0 = W.tab_invw[7];
+    if (!ZERO) { W.publish(xr); __syncthreads(); }
 #pragma unroll
-        for (int da = 0; da < 4; da++) {
-            const T *pa = row + cA * PL, *pb = row + (1 - cA) * PL;
-            T v = (pa[kA] + pb[kD]) + T(3) * (pb[kB] + pa[kC]);
-            acc += (da == 1 || da == 2) ? T(3) * v : v;
-            row += TK;
-            cA ^= 1;
-        }
-        bc[(long)(Jc + 1) * A.pitchc + I + 1] = (TC)acc;
+    for (int hs = 0; hs < 2 * NU; hs++) {
+        if (ZERO && hs == 0) W.template relax_open<true>(0, 0, rp, fr, xr, dinv0);
+        else W.template relax_open<false>(hs & 1, ZERO ? hs : hs + 1, rp, fr, xr, dinv0);
+        __syncthreads();
     }
+    W.residual_open(H - 1, rp, fr, xr, diag0, invw0);
+    {
+        const long g0 = L.base(wj0 + warp, wi0 + 2 * k);
+        const long st = (long)TILE_WARPS * L.stride();
+#pragma unroll
+        for (int r = 0; r < RO; r++) {
+            const int a = warp + r * TILE_WARPS;
+            if (a < H || a >= WJ - H) continue;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int h = c ^ rp, b = 2 * k + h;
+                if (b < H || b >= TW - H) continue;
+                xout[g0 + r * st + h] = (TX)xr[r][c];
+            }
+        }
+    }
+    __syncthreads();
+    restrict_tile<T, TC, true, WJ, H>(W, L, A, bc, tj0, ti0, par0);
 }
 
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
@@ -488,25 +628,35 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
     const int par0 = (wj0 + wi0) & 1;
     double fshift = 0.0;
     if constexpr (FINE) {
+        // every global load is issued before the set-up work: the tables (an fp64
+        // division) and the mean are computed while the window is in flight
+        constexpr int RO = WJ / TILE_WARPS;
+        const bool inside = A.allow_open && L.inside(wj0, wi0, WJ, TW);     // block-uniform
+        TF fv[RO][2];
+        TX xv[RO][2];
+        uint8_t bits[RO][2];
+        if (sumr_slot >= 0) fshift = scal[sumr_slot];
+        if (inside) W.template fetch_inside<!ZERO>(L, xin, fin, wj0, wi0, fv, xv, bits);
         W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
         W.fill_tables(&L.F, L.dirichlet());
-        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
-    } else W.fill_tables(nullptr, L.dirichlet());
-    if constexpr (FINE) {
-        int open = 0;
-        if (A.allow_open && L.inside(wj0, wi0, WJ, TW))      // block-uniform
-            open = W.template load_inside<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        else
+        fshift *= inv_n;
+        if (inside) {
+            if (__syncthreads_and(W.all_open(bits))) {
+                T fr[RO][2], xr[RO][2];
+                W.template own<false>(fv, xv, fscale, fshift, (par0 + (threadIdx.x >> 5)) & 1, fr, xr);
+                down_open<T, TX, TC, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0, fr, xr);
+                return;
+            }
+            W.template stash<false>(fv, xv, bits, fscale, fshift, par0);
+        } else {
             W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        if (__syncthreads_and(open)) {
-            down_body<true, T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
-            return;
         }
     } else {
+        W.fill_tables(nullptr, L.dirichlet());
         W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        __syncthreads();
     }
-    down_body<false, T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
+    __syncthreads();
+    down_body<T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
 }
 
 // ---------------------------------------------------------------------------
@@ -517,7 +667,7 @@ struct UpArgs {
     int allow_open;
 };
 
-template <bool OPEN, typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
 __device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, const TC *XC, TX *__restrict__ xout,
                                         const TF *__restrict__ fin, double fscale, double fshift, int tj0, int ti0,
                                         double (&acc)[2]) {
@@ -527,8 +677,6 @@ __device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, co
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
-    T dinv0 = T(0), invw0 = T(0);
-    if constexpr (OPEN) { dinv0 = W.tab_dinv[31]; invw0 = W.tab_invw[7]; }
     // ---- prolongation on the whole window
 #pragma unroll
     for (int r = 0; r < WJ / TILE_WARPS; r++) {
@@ -538,70 +686,122 @@ __device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, co
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int b = 2 * k + h, p = W.at(rp ^ h, a, k);
-            T w = invw0;
-            if constexpr (!OPEN) {
-                uint8_t bits = W.B[p];
-                if (!(bits & NB_SELF)) continue;
-                w = W.tab_invw[bits >> 5];
-            }
+            uint8_t bits = W.B[p];
+            if (!(bits & NB_SELF)) continue;
             int i = wi0 + b;
             int I0 = (i >> 1) - ci0, In = I0 + ((i & 1) ? 1 : -1);
             T v = prol_val((T)XC[J0 * CI + I0], (T)XC[Jn * CI + I0], (T)XC[J0 * CI + In], (T)XC[Jn * CI + In]);
-            W.X[p] = mul_add(v, w, W.X[p]);
+            W.X[p] = mul_add(v, W.tab_invw[bits >> 5], W.X[p]);
         }
     }
     __syncthreads();
     // ---- NU sweeps, black then red
 #pragma unroll
     for (int hs = 0; hs < 2 * NU; hs++) {
-        W.template relax<false, OPEN>(1 - (hs & 1), hs + 1, par0, dinv0);
+        W.template relax<false>(1 - (hs & 1), hs + 1, par0);
         __syncthreads();
     }
     // ---- write the interior (+ dots)
-    if constexpr (OPEN) {
-        const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
-        const long st = (long)TILE_WARPS * L.stride();
+    const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
 #pragma unroll
-        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
-            int a = H + warp + r * TILE_WARPS;
-            if (a >= WJ - H) break;
-            int rp = (par0 + a) & 1;
-            const bool own = L.owned(wj0 + a);
+    for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
+        int a = H + warp + r * TILE_WARPS;
+        if (a >= WJ - H) break;
+        int rp = (par0 + a) & 1, j = wj0 + a;
+        long rb = L.row(j);
+        if (rb < 0) continue;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int b = 2 * k + h;
-                if (b < H || b >= TW - H) continue;
-                const long g = g0 + r * st + h;
-                T xv = W.X[W.at(rp ^ h, a, k)];
-                xout[g] = (TX)xv;
-                if (DOT && own) {
-                    double fv = __fma_rn(fscale, (double)fin[g], -fshift);
-                    acc[0] = __fma_rn(fv, (double)xv, acc[0]); acc[1] += (double)xv;
-                }
+        for (int h = 0; h < 2; h++) {
+            int b = 2 * k + h, p = W.at(rp ^ h, a, k), ch = h ? c1 : c0;
+            if (b < H || b >= TW - H || ch < 0) continue;
+            if (!(W.B[p] & NB_SELF)) continue;
+            if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
+            T xv = W.X[p];
+            xout[rb + ch] = (TX)xv;
+            if (DOT && L.owned(j)) {
+                // the dot uses the fp64 residual, not its narrowed copy in shared memory
+                double fv = __fma_rn(fscale, (double)fin[rb + ch], -fshift);
+                acc[0] = __fma_rn(fv, (double)xv, acc[0]); acc[1] += (double)xv;
             }
         }
-    } else {
-        const int c0 = L.col(wi0 + 2 * k), c1 = L.col(wi0 + 2 * k + 1);
+    }
+}
+
+// open tile: registers fr / xr hold the thread's 2 x RO points
+template <typename T, typename TX, typename TF, typename TC, bool DOT, int NU, int WJ, class Lev>
+__device__ __forceinline__ void up_open(Window<T, true, WJ> &W, const Lev &L, const TC *XC, TX *__restrict__ xout,
+                                        const TF *__restrict__ fin, double fscale, double fshift, int tj0,
+                                        int ti0, const T (&fr)[WJ / TILE_WARPS][2], T (&xr)[WJ / TILE_WARPS][2],
+                                        double (&acc)[2]) {
+    constexpr int H = halo_up(NU), RO = WJ / TILE_WARPS;
+    constexpr int CI = TW / 2 + 3;
+    const int wj0 = tj0 - H, wi0 = ti0 - H;
+    const int par0 = (wj0 + wi0) & 1;
+    const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+    const int rp = (par0 + warp) & 1;
+    const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
+    const T dinv0 = W.tab_dinv[31], invw0 = W.tab_invw[7];
+    // ---- prolongation of the thread's own points
+    {
+        // columns 2k (h = 0) and 2k+1 (h = 1): own parent I0, the other parent one column to the side
+        const int i0 = wi0 + 2 * k;
+        const int I0a = (i0 >> 1) - ci0, Ina = I0a + ((i0 & 1) ? 1 : -1);
+        const int I0b = ((i0 + 1) >> 1) - ci0, Inb = I0b + (((i0 + 1) & 1) ? 1 : -1);
 #pragma unroll
-        for (int r = 0; r < Window<T, FINE, WJ>::ROWS_PER_WARP; r++) {
-            int a = H + warp + r * TILE_WARPS;
-            if (a >= WJ - H) break;
-            int rp = (par0 + a) & 1, j = wj0 + a;
-            long rb = L.row(j);
-            if (rb < 0) continue;
+        for (int r = 0; r < RO; r++) {
+            const int j = wj0 + warp + r * TILE_WARPS;
+            const int J0 = (j >> 1) - cj0, Jn = J0 + ((j & 1) ? 1 : -1);
+            const TC *r0 = XC + J0 * CI, *rn = XC + Jn * CI;
+            T va = prol_val((T)r0[I0a], (T)rn[I0a], (T)r0[Ina], (T)rn[Ina]);
+            T vb = prol_val((T)r0[I0b], (T)rn[I0b], (T)r0[Inb], (T)rn[Inb]);
+            // column h holds colour h ^ rp
+            T v0 = rp ? vb : va, v1 = rp ? va : vb;
+            xr[r][0] = mul_add(v0, invw0, xr[r][0]);
+            xr[r][1] = mul_add(v1, invw0, xr[r][1]);
+        }
+    }
+    W.publish(xr);
+    __syncthreads();
+    // ---- NU sweeps, black then red
+#pragma unroll
+    for (int hs = 0; hs < 2 * NU; hs++) {
+        W.template relax_open<false>(1 - (hs & 1), hs + 1, rp, fr, xr, dinv0);
+        __syncthreads();
+    }
+    // ---- write the interior (+ dots): from shared memory, with the generic
+    // path's thread-to-row map, so that a CTA's partial sums (and with them the
+    // CG scalars) do not depend on which path it took.  The fp64 residual of the
+    // dots is re-read in one batch (all loads in flight) before anything is stored.
+    constexpr int RW = Window<T, true, WJ>::ROWS_PER_WARP;
+    const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
+    const long st = (long)TILE_WARPS * L.stride();
+    TF fq[RW][2];
+    if (DOT) {
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+            const bool rowok = H + warp + r * TILE_WARPS < WJ - H;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                int b = 2 * k + h, p = W.at(rp ^ h, a, k), ch = h ? c1 : c0;
-                if (b < H || b >= TW - H || ch < 0) continue;
-                if (!(W.B[p] & NB_SELF)) continue;
-                if (wi0 + b >= L.nx()) continue;   // periodic images are another tile's
-                T xv = W.X[p];
-                xout[rb + ch] = (TX)xv;
-                if (DOT && L.owned(j)) {
-                    // the dot uses the fp64 residual, not its narrowed copy in shared memory
-                    double fv = __fma_rn(fscale, (double)fin[rb + ch], -fshift);
-                    acc[0] = __fma_rn(fv, (double)xv, acc[0]); acc[1] += (double)xv;
-                }
+                const int b = 2 * k + h;
+                fq[r][h] = (rowok && b >= H && b < TW - H) ? fin[g0 + r * st + h] : TF(0);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; r++) {
+        const int a = H + warp + r * TILE_WARPS;
+        if (a >= WJ - H) break;
+        const int rpa = (par0 + a) & 1;
+        const bool mine = L.owned(wj0 + a);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = 2 * k + h;
+            if (b < H || b >= TW - H) continue;
+            const T xv = W.X[W.at(rpa ^ h, a, k)];
+            xout[g0 + r * st + h] = (TX)xv;
+            if (DOT && mine) {
+                double f = __fma_rn(fscale, (double)fq[r][h], -fshift);
+                acc[0] = __fma_rn(f, (double)xv, acc[0]); acc[1] += (double)xv;
             }
         }
     }
@@ -623,49 +823,69 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     double fshift = 0.0;
-    if constexpr (FINE) {
-        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        W.fill_tables(&L.F, L.dirichlet());
-        if (sumr_slot >= 0) fshift = scal[sumr_slot] * inv_n;
-    } else W.fill_tables(nullptr, L.dirichlet());
-    // ---- coarse window
+    if (FINE && sumr_slot >= 0) fshift = scal[sumr_slot];
+    // ---- coarse window: global -> shared asynchronously (no registers held)
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
     const int Jc0 = cj0 + L.pj_off();
     if (Jc0 >= 0 && Jc0 + CJ <= A.nyc && ci0 >= 0 && ci0 + CI <= A.nxc) {   // block-uniform: no bounds, no wrap
         const TC *src = xc + (long)(Jc0 + 1) * A.pitchc + ci0 + 1;
         for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
             int a = t / CI, b = t - a * CI;
-            XC[t] = src[a * A.pitchc + b];
+            cp_async<sizeof(TC)>(XC + t, src + a * A.pitchc + b);
         }
     } else {
         for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
             int a = t / CI, b = t - a * CI;
             int J = Jc0 + a, I = ci0 + b;
-            TC v = TC(0);
-            if (J >= 0 && J < A.nyc) {
+            bool ok = J >= 0 && J < A.nyc;
+            if (ok) {
                 if (A.periodic_c) I = wrap_col(I, A.nxc);
-                if (I >= 0 && I < A.nxc) v = xc[(long)(J + 1) * A.pitchc + I + 1];
+                ok = I >= 0 && I < A.nxc;
             }
-            XC[t] = v;
+            if (ok) cp_async<sizeof(TC)>(XC + t, xc + (long)(J + 1) * A.pitchc + I + 1);
+            else XC[t] = TC(0);
         }
     }
     double acc[2] = {0.0, 0.0};
     bool done = false;
     if constexpr (FINE) {
-        int open = 0;
-        if (A.allow_open && L.inside(wj0, wi0, WJ, TW))      // block-uniform
-            open = W.template load_inside<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        else
+        constexpr int RO = WJ / TILE_WARPS;
+        const bool inside = A.allow_open && L.inside(wj0, wi0, WJ, TW);     // block-uniform
+        TF fv[RO][2];
+        TX xv[RO][2];
+        uint8_t bits[RO][2];
+        if (inside) {
+            W.fetch_x_async(L, xin, wj0, wi0, par0);
+            W.template fetch_inside<false>(L, xin, fin, wj0, wi0, fv, xv, bits);
+        }
+        // set-up work while the window is in flight
+        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+        W.fill_tables(&L.F, L.dirichlet());
+        fshift *= inv_n;
+        if (inside) {
+            const bool mine = W.all_open(bits);
+            cp_async_wait_all();
+            if (__syncthreads_and(mine)) {
+                T fr[RO][2], xr[RO][2];
+                W.template own<true>(fv, xv, fscale, fshift, (par0 + (threadIdx.x >> 5)) & 1, fr, xr);
+                up_open<T, TX, TF, TC, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, fr, xr, acc);
+                done = true;
+            } else {
+                W.template stash<true>(fv, xv, bits, fscale, fshift, par0);
+            }
+        } else {
             W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        if (__syncthreads_and(open)) {
-            up_body<true, T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
-            done = true;
+            cp_async_wait_all();
         }
     } else {
+        W.fill_tables(nullptr, L.dirichlet());
         W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        __syncthreads();
+        cp_async_wait_all();
     }
-    if (!done) up_body<false, T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
+    if (!done) {
+        __syncthreads();
+        up_body<T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
+    }
     if (DOT) grid_reduce<OpSum, 2>(acc, part, count, out);
 }
 

@@ -15,6 +15,8 @@ struct OpMax {
     __device__ static double ap(double a, double b) { return fmax(a, b); }
 };
 
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 template <class Op>
 __device__ __forceinline__ double warp_reduce(double v) {
 #pragma unroll
@@ -59,13 +61,17 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *part, unsig
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NV; k++) part[(size_t)k * nblocks + bid] = v[k];
-        __threadfence();
+        // release the partials / acquire everybody else's: fence.acq_rel (MEMBAR.ALL.GPU)
+        // is enough for this message-passing pattern and much cheaper than the
+        // sequentially consistent fence __threadfence() compiles to (MEMBAR.SC.GPU),
+        // which every thread of the CTA would sit behind at the barrier below
+        fence_acq_rel_gpu();
         unsigned t = atomicAdd(count, 1u);
         last = (t == nblocks - 1);
+        if (t == nblocks - 1) fence_acq_rel_gpu();
     }
     __syncthreads();
     if (!last) return;
-    __threadfence();
     int nt = blockDim.x * blockDim.y;
     double acc[NV];
 #pragma unroll
