@@ -34,7 +34,10 @@ enum : uint8_t {
     NB_W = 2, NB_E = 4, NB_S = 8, NB_N = 16,   // coupling to that neighbour is open
     NB_PJ = 32,    // coarse parent (Jn, I0) is fluid      (prolongation weights)
     NB_PI = 64,    //               (J0, In)
-    NB_PJI = 128   //               (Jn, In)
+    NB_PJI = 128,  //               (Jn, In)
+    // coarse levels (their codes carry no face bits): the point and its four faces have
+    // the level's regular coefficients -- no wall, no mask nearby (open tiles, mg_tiles.cuh)
+    NB_REG = 2
 };
 
 // element type of the coarse multigrid levels: the coarse-grid correction only
@@ -77,6 +80,7 @@ struct Level {
     CT *cx = nullptr, *cy = nullptr, *dinv = nullptr;
     double *mass = nullptr, *wall = nullptr;   // set-up only
     uint8_t *code = nullptr;
+    CT cx0 = 0, cy0 = 0, dinv0 = 0;            // coefficients of a regular point (NB_REG)
 };
 
 // y-slab decomposition: one context per GPU/process.  Every array of a rank

@@ -580,6 +580,28 @@ __global__ void k_build_dinv(Level L, int periodic) {
     if (d == 0.0) L.code[c] = 0;
 }
 
+// NB_REG: the point is an unknown whose four couplings and inverse diagonal are
+// the level's regular values (mg_tiles.cuh, open tiles).  Runs when every
+// coefficient of the level, ghost rows included, is final.
+__global__ void k_mark_regular(Level L, int periodic, CT cx0, CT cy0, CT dinv0) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= L.nx || J >= L.ny) return;
+    long c = (long)(J + 1) * L.pitch + I + 1;
+    long e = c + 1;
+    if (periodic && I == L.nx - 1) e = c - (L.nx - 1);
+    else if (I == L.nx - 1) return;                      // closed domain: no regular east face
+    uint8_t code = L.code[c];
+    if (!(code & NB_SELF)) return;
+    if (L.cx[c] == cx0 && L.cx[e] == cx0 && L.cy[c] == cy0 && L.cy[c + L.pitch] == cy0 && L.dinv[c] == dinv0)
+        L.code[c] = code | NB_REG;
+}
+
+// regular coefficients of level l >= 1 (k_coarsen0 / k_coarsen / k_build_dinv away from
+// walls and masks: couplings stay cx, cy; the mass term quadruples per level)
+static void mark_regular(f2d_ctx *c, const FineView &F, std::vector<Level> &lev, int first, int last, int level0,
+                         int xper);
+
 // which of the three non-own parents of each fine cell are unknowns on the coarse level
 __device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, int periodic, int pj_off) {
     int J0, Jn, I0, In;
@@ -635,6 +657,22 @@ static dim3 cg_grid(const f2d_ctx *c, const FineView &F) {
     return dim3(gx, gy);
 }
 static dim3 grd(int nx, int ny) { return dim3((nx + 63) / 64, (ny + 3) / 4); }
+
+static void mark_regular(f2d_ctx *c, const FineView &F, std::vector<Level> &lev, int first, int last, int level0,
+                         int xper) {
+    // lev[first..last] are multigrid levels level0 + (l - first)
+    for (int l = first; l <= last; l++) {
+        Level &L = lev[l];
+        const int lvl = level0 + (l - first);
+        L.cx0 = (CT)F.cx; L.cy0 = (CT)F.cy;
+        double mass = F.shift;
+        for (int k = 0; k < lvl; k++) mass = ((mass + mass) + mass) + mass;      // the order k_coarsen adds them in
+        const CT faces = ((L.cx0 + L.cx0) + L.cy0) + L.cy0;      // k_build_dinv adds the four CT couplings first
+        double diag = (double)faces + mass + 0.0;
+        L.dinv0 = diag > 0.0 ? (CT)(1.0 / diag) : CT(0);
+        k_mark_regular<<<grd(L.nx, L.ny), blk(), 0, c->stream>>>(L, xper, L.cx0, L.cy0, L.dinv0);
+    }
+}
 
 static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
     CoarseView V;
@@ -842,6 +880,7 @@ int mg_build(f2d_ctx *c, int which) {
         k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper, 0);
         LAUNCH_CHECK(c);
     }
+    if (M.tail > 1) { mark_regular(c, F, M.lev, 1, M.tail - 1, 1, xper); LAUNCH_CHECK(c); }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t l = 1; l < M.lev.size(); l++) {   // set-up only arrays
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
@@ -984,6 +1023,7 @@ static int mg_build_slab(f2d_ctx *c, int which) {
         k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper, pj);
         LAUNCH_CHECK(c);
     }
+    if (T > 1) { mark_regular(c, F, M.lev, 1, T - 1, 1, xper); LAUNCH_CHECK(c); }
     // global tail hierarchy: level T gathered from the owners, coarser ones derived
     {
         const Level &LT = M.lev[T];
@@ -1212,6 +1252,7 @@ static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, i
     CoarseArrays<CT> A;
     A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.dirichlet = dirichlet; A.pj_off = pj_off;
     A.cx = L.cx; A.cy = L.cy; A.dinv = L.dinv; A.code = L.code;
+    A.cx0 = L.cx0; A.cy0 = L.cy0; A.dinv0 = L.dinv0;
     return A;
 }
 
@@ -1276,7 +1317,7 @@ static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
     dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
     const Level &C = M.lev[l + 1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x, Lv.b, 1.0, c->d_scal, -1, 0.0,
-                                               DownArgs{C.ny, C.nx, C.pitch, 0}, C.b);
+                                               DownArgs{C.ny, C.nx, C.pitch, allow_open_tiles()}, C.b);
     LAUNCH_CHECK(c);
     return F2D_OK;
 }
@@ -1293,7 +1334,7 @@ static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
     const Level &C = M.lev[l + 1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x2, Lv.b, 1.0, c->d_scal, -1, 0.0,
-                                               UpArgs{C.ny, C.nx, C.pitch, M.fine.periodic, 0}, level_result(M, l + 1),
+                                               UpArgs{C.ny, C.nx, C.pitch, M.fine.periodic, allow_open_tiles()}, level_result(M, l + 1),
                                                nullptr, nullptr, nullptr);
     LAUNCH_CHECK(c);
     return F2D_OK;

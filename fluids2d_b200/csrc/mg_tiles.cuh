@@ -56,6 +56,7 @@ struct CoarseArrays {       // level l >= 1, halo-padded (ny+2) x pitch
     int ny, nx, pitch, periodic, dirichlet, pj_off;
     const T *cx, *cy, *dinv;
     const uint8_t *code;
+    T cx0, cy0, dinv0;      // coefficients of a regular point (NB_REG): all faces open, no wall, no mask nearby
 };
 
 // sum of the four neighbour contributions / Gauss-Seidel update / residual with
@@ -65,6 +66,14 @@ __device__ __forceinline__ float nb_sum(float cx, float cy, float xw, float xe, 
 }
 __device__ __forceinline__ double nb_sum(double cx, double cy, double xw, double xe, double xs, double xn) {
     return __fma_rn(cx, __dadd_rn(xw, xe), __dmul_rn(cy, __dadd_rn(xs, xn)));
+}
+// four couplings (coarse levels): w, e, s, n in this order in both paths
+__device__ __forceinline__ float nb_sum4(float cw, float xw, float ce, float xe, float cs, float xs, float cn, float xn) {
+    return __fmaf_rn(cw, xw, __fmaf_rn(ce, xe, __fmaf_rn(cs, xs, __fmul_rn(cn, xn))));
+}
+__device__ __forceinline__ double nb_sum4(double cw, double xw, double ce, double xe, double cs, double xs, double cn,
+                                          double xn) {
+    return __fma_rn(cw, xw, __fma_rn(ce, xe, __fma_rn(cs, xs, __dmul_rn(cn, xn))));
 }
 __device__ __forceinline__ float gs_new(float f, float off, float dinv) { return __fmul_rn(__fadd_rn(f, off), dinv); }
 __device__ __forceinline__ double gs_new(double f, double off, double dinv) { return __dmul_rn(__dadd_rn(f, off), dinv); }
@@ -136,6 +145,8 @@ struct FineLevel {
     }
     __device__ __forceinline__ long base(int j, int i) const { return (long)(F.oj + j) * F.n1 + F.oi + i; }
     __device__ __forceinline__ int stride() const { return F.n1; }
+    __device__ __forceinline__ const uint8_t *bits_ptr() const { return F.nb; }
+    static constexpr unsigned FULL = 0xFFu;     // unknown, four open faces, three fluid parents
 };
 
 template <typename T>
@@ -154,9 +165,13 @@ struct CoarseLevel {
         if (A.periodic) return wrap_col(i, A.nx);
         return (i < 0 || i >= A.nx) ? -1 : i;
     }
-    __device__ __forceinline__ bool inside(int, int, int, int) const { return false; }   // generic path only
+    __device__ __forceinline__ bool inside(int j0, int i0, int nj, int ni) const {
+        return j0 >= 0 && j0 + nj <= A.ny && i0 >= 0 && i0 + ni <= A.nx;
+    }
     __device__ __forceinline__ long base(int j, int i) const { return (long)(j + 1) * A.pitch + 1 + i; }
     __device__ __forceinline__ int stride() const { return A.pitch; }
+    __device__ __forceinline__ const uint8_t *bits_ptr() const { return A.code; }
+    static constexpr unsigned FULL = NB_SELF | NB_REG | NB_PJ | NB_PI | NB_PJI;
 };
 
 // ---- shared-memory window -----------------------------------------------------
@@ -232,10 +247,10 @@ struct Window {
                 const T *q = xq + r * S;
                 T xw = q[-1], xe = q[0], xs = q[-o - TK], xn = q[-o + TK];
                 if constexpr (FINE) off = nb_sum(cxf, cyf, xw, xe, xs, xn);
-                else off = CX[p0 + r * S] * xw + CX[q0 + o + r * S] * xe + CY[p0 + r * S] * xs + CY[q0 + TK + r * S] * xn;
+                else off = nb_sum4(CX[p0 + r * S], xw, CX[q0 + o + r * S], xe, CY[p0 + r * S], xs, CY[q0 + TK + r * S], xn);
             }
             if constexpr (FINE) xp[r * S] = gs_new(fp[r * S], off, tab_dinv[B[p0 + r * S] & 31]);
-            else xp[r * S] = (fp[r * S] + off) * DI[p0 + r * S];
+            else xp[r * S] = gs_new(fp[r * S], off, DI[p0 + r * S]);
         }
     }
 
@@ -263,7 +278,7 @@ struct Window {
                     off = nb_sum(cxf, cyf, xw, xe, xs, xn);
                     diag = tab_diag[bits & 31];
                 } else {
-                    off = CX[p] * xw + CX[q0 + r * S] * xe + CY[p] * xs + CY[q0 - o + TK + r * S] * xn;
+                    off = nb_sum4(CX[p], xw, CX[q0 + r * S], xe, CY[p], xs, CY[q0 - o + TK + r * S], xn);
                     T di = DI[p];
                     diag = di != T(0) ? T(1) / di : T(0);
                 }
@@ -331,7 +346,8 @@ struct Window {
         }
     }
 
-    // ---- open tiles (FINE): fixed ownership, f and x in registers -------------
+    // ---- open tiles: fixed ownership, f and x in registers --------------------
+    // (COARSE: cxf / cyf hold the level's regular couplings)
     // Thread (warp w, lane k) owns rows w, w+16, ... x columns 2k, 2k+1 for the
     // whole leg.  Its rows share one parity rp, so its colour-c points sit in
     // column 2k + (c ^ rp); registers are indexed [row][colour].  Of the four
@@ -346,8 +362,8 @@ struct Window {
     __device__ __forceinline__ void fetch_inside(const Lev &L, const TX *__restrict__ xin, const TF *__restrict__ fin,
                                                  int wj0, int wi0, TF (&fv)[RO][2], TX (&xv)[RO][2],
                                                  uint8_t (&bits)[RO][2]) {
-        static_assert(FINE, "open tiles exist on the fine level only");
         const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+        const uint8_t *__restrict__ nb = L.bits_ptr();
         const long g0 = L.base(wj0 + warp, wi0 + 2 * k);
         const long st = (long)TILE_WARPS * L.stride();
 #pragma unroll
@@ -355,7 +371,7 @@ struct Window {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const long g = g0 + r * st + h;
-                bits[r][h] = L.F.nb[g];
+                bits[r][h] = nb[g];
                 fv[r][h] = fin[g];
                 xv[r][h] = TX(0);
                 if (LOAD_X) xv[r][h] = xin[g];
@@ -376,12 +392,12 @@ struct Window {
             cp_async<sizeof(T)>(X + at(rp ^ 1, warp + r * TILE_WARPS, k), src + r * st + 1);
         }
     }
-    // every mask byte this thread fetched is 0xFF
-    __device__ __forceinline__ static bool all_open(const uint8_t (&bits)[RO][2]) {
+    // every mask byte this thread fetched has all the bits of `full`
+    __device__ __forceinline__ static bool all_open(const uint8_t (&bits)[RO][2], unsigned full) {
         unsigned all = 0xFFu;
 #pragma unroll
         for (int r = 0; r < RO; r++) all &= bits[r][0] & bits[r][1];
-        return all == 0xFFu;
+        return (all & full) == full;
     }
 
     // registers -> shared memory, exactly what load() leaves (an inside tile that is not open)
@@ -453,7 +469,8 @@ struct Window {
             if (!NO_NEIGHBOURS) {
                 const T *q = xq + r * S;
                 T xl = q[side], xs = q[-TK], xn = q[TK], mine = xr[r][1 - c];
-                off = nb_sum(cxf, cyf, mine, xl, xs, xn);     // xw + xe commutes: no need to know which is which
+                if constexpr (FINE) off = nb_sum(cxf, cyf, mine, xl, xs, xn);     // xw + xe commutes: no need to know which is which
+                else off = nb_sum4(cxf, o ? mine : xl, cxf, o ? xl : mine, cyf, xs, cyf, xn);
             }
             T v = gs_new(fr[r][c], off, dinv0);
             xr[r][c] = v;
@@ -479,7 +496,10 @@ struct Window {
                 if (a < m || a >= WJ - m) continue;
                 const T *q = xq + r * S;
                 T xl = q[side], xs = q[-TK], xn = q[TK], mine = xr[r][1 - c];
-                fp[r * S] = res_val(fr[r][c], diag0, xr[r][c], nb_sum(cxf, cyf, mine, xl, xs, xn), invw0);
+                T off;
+                if constexpr (FINE) off = nb_sum(cxf, cyf, mine, xl, xs, xn);
+                else off = nb_sum4(cxf, o ? mine : xl, cxf, o ? xl : mine, cyf, xs, cyf, xn);
+                fp[r * S] = res_val(fr[r][c], diag0, xr[r][c], off, invw0);
             }
         }
     }
@@ -577,8 +597,27 @@ __device__ __forceinline__ void down_body(Window<T, FINE, WJ> &W, const Lev &L, 
 }
 
 // open tile: registers fr / xr hold the thread's 2 x RO points
-template <typename T, typename TX, typename TC, bool ZERO, int NU, int WJ, class Lev>
-__device__ __forceinline__ void down_open(Window<T, true, WJ> &W, const Lev &L, TX *__restrict__ xout,
+template <typename T>
+struct OpenConst { T dinv0, diag0, invw0; };
+
+// regular-point constants: FINE from the tables, COARSE from the level (the generic
+// path's expressions, so that both give the same bits)
+template <typename T, bool FINE, int WJ, class Lev>
+__device__ __forceinline__ OpenConst<T> open_const(Window<T, FINE, WJ> &W, const Lev &L) {
+    OpenConst<T> K;
+    if constexpr (FINE) {
+        K.dinv0 = W.tab_dinv[31]; K.diag0 = W.tab_diag[31];
+    } else {
+        W.cxf = L.A.cx0; W.cyf = L.A.cy0;
+        K.dinv0 = L.A.dinv0;
+        K.diag0 = K.dinv0 != T(0) ? T(1) / K.dinv0 : T(0);
+    }
+    K.invw0 = W.tab_invw[7];
+    return K;
+}
+
+template <typename T, typename TX, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
+__device__ __forceinline__ void down_open(Window<T, FINE, WJ> &W, const Lev &L, TX *__restrict__ xout,
                                           const DownArgs &A, TC *__restrict__ bc, int tj0, int ti0,
                                           const T (&fr)[WJ / TILE_WARPS][2], T (&xr)[WJ / TILE_WARPS][2]) {
     constexpr int H = halo_down(NU, ZERO), RO = WJ / TILE_WARPS;
@@ -586,7 +625,8 @@ __device__ __forceinline__ void down_open(Window<T, true, WJ> &W, const Lev &L, 
     const int par0 = (wj0 + wi0) & 1;
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     const int rp = (par0 + warp) & 1;
-    const T dinv0 = W.tab_dinv[31], diag0 = W.tab_diag[31], invw0 = W.tab_invw[7];
+    const OpenConst<T> K = open_const<T, FINE, WJ>(W, L);
+    const T dinv0 = K.dinv0, diag0 = K.diag0, invw0 = K.invw0;
     if (!ZERO) { W.publish(xr); __syncthreads(); }
 #pragma unroll
     for (int hs = 0; hs < 2 * NU; hs++) {
@@ -611,7 +651,7 @@ __device__ __forceinline__ void down_open(Window<T, true, WJ> &W, const Lev &L, 
         }
     }
     __syncthreads();
-    restrict_tile<T, TC, true, WJ, H>(W, L, A, bc, tj0, ti0, par0);
+    restrict_tile<T, TC, FINE, WJ, H>(W, L, A, bc, tj0, ti0, par0);
 }
 
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
@@ -627,7 +667,7 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
     const int wj0 = tj0 - H, wi0 = ti0 - H;
     const int par0 = (wj0 + wi0) & 1;
     double fshift = 0.0;
-    if constexpr (FINE) {
+    {
         // every global load is issued before the set-up work: the tables (an fp64
         // division) and the mean are computed while the window is in flight
         constexpr int RO = WJ / TILE_WARPS;
@@ -635,25 +675,27 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
         TF fv[RO][2];
         TX xv[RO][2];
         uint8_t bits[RO][2];
-        if (sumr_slot >= 0) fshift = scal[sumr_slot];
+        if (FINE && sumr_slot >= 0) fshift = scal[sumr_slot];
         if (inside) W.template fetch_inside<!ZERO>(L, xin, fin, wj0, wi0, fv, xv, bits);
-        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        W.fill_tables(&L.F, L.dirichlet());
+        if constexpr (FINE) {
+            W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+            W.fill_tables(&L.F, L.dirichlet());
+        } else W.fill_tables(nullptr, L.dirichlet());
         fshift *= inv_n;
         if (inside) {
-            if (__syncthreads_and(W.all_open(bits))) {
+            if (__syncthreads_and(W.all_open(bits, Lev::FULL))) {
                 T fr[RO][2], xr[RO][2];
                 W.template own<false>(fv, xv, fscale, fshift, (par0 + (threadIdx.x >> 5)) & 1, fr, xr);
-                down_open<T, TX, TC, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0, fr, xr);
+                down_open<T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0, fr, xr);
                 return;
             }
-            W.template stash<false>(fv, xv, bits, fscale, fshift, par0);
+            // inside but not open: FINE has everything it needs in registers, COARSE
+            // fetches the coefficient arrays as well
+            if constexpr (FINE) W.template stash<false>(fv, xv, bits, fscale, fshift, par0);
+            else W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
         } else {
             W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
         }
-    } else {
-        W.fill_tables(nullptr, L.dirichlet());
-        W.template load<!ZERO>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
     }
     __syncthreads();
     down_body<T, TX, TC, FINE, ZERO, NU, WJ>(W, L, xout, A, bc, tj0, ti0);
@@ -728,8 +770,8 @@ __device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, co
 }
 
 // open tile: registers fr / xr hold the thread's 2 x RO points
-template <typename T, typename TX, typename TF, typename TC, bool DOT, int NU, int WJ, class Lev>
-__device__ __forceinline__ void up_open(Window<T, true, WJ> &W, const Lev &L, const TC *XC, TX *__restrict__ xout,
+template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
+__device__ __forceinline__ void up_open(Window<T, FINE, WJ> &W, const Lev &L, const TC *XC, TX *__restrict__ xout,
                                         const TF *__restrict__ fin, double fscale, double fshift, int tj0,
                                         int ti0, const T (&fr)[WJ / TILE_WARPS][2], T (&xr)[WJ / TILE_WARPS][2],
                                         double (&acc)[2]) {
@@ -740,7 +782,8 @@ __device__ __forceinline__ void up_open(Window<T, true, WJ> &W, const Lev &L, co
     const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
     const int rp = (par0 + warp) & 1;
     const int cj0 = (wj0 >> 1) - 1, ci0 = (wi0 >> 1) - 1;
-    const T dinv0 = W.tab_dinv[31], invw0 = W.tab_invw[7];
+    const OpenConst<T> K = open_const<T, FINE, WJ>(W, L);
+    const T dinv0 = K.dinv0, invw0 = K.invw0;
     // ---- prolongation of the thread's own points
     {
         // columns 2k (h = 0) and 2k+1 (h = 1): own parent I0, the other parent one column to the side
@@ -772,7 +815,7 @@ __device__ __forceinline__ void up_open(Window<T, true, WJ> &W, const Lev &L, co
     // path's thread-to-row map, so that a CTA's partial sums (and with them the
     // CG scalars) do not depend on which path it took.  The fp64 residual of the
     // dots is re-read in one batch (all loads in flight) before anything is stored.
-    constexpr int RW = Window<T, true, WJ>::ROWS_PER_WARP;
+    constexpr int RW = Window<T, FINE, WJ>::ROWS_PER_WARP;
     const long g0 = L.base(wj0 + H + warp, wi0 + 2 * k);
     const long st = (long)TILE_WARPS * L.stride();
     TF fq[RW][2];
@@ -848,7 +891,7 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
     }
     double acc[2] = {0.0, 0.0};
     bool done = false;
-    if constexpr (FINE) {
+    {
         constexpr int RO = WJ / TILE_WARPS;
         const bool inside = A.allow_open && L.inside(wj0, wi0, WJ, TW);     // block-uniform
         TF fv[RO][2];
@@ -859,28 +902,27 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
             W.template fetch_inside<false>(L, xin, fin, wj0, wi0, fv, xv, bits);
         }
         // set-up work while the window is in flight
-        W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
-        W.fill_tables(&L.F, L.dirichlet());
+        if constexpr (FINE) {
+            W.cxf = (T)L.F.cx; W.cyf = (T)L.F.cy;
+            W.fill_tables(&L.F, L.dirichlet());
+        } else W.fill_tables(nullptr, L.dirichlet());
         fshift *= inv_n;
         if (inside) {
-            const bool mine = W.all_open(bits);
+            const bool mine = W.all_open(bits, Lev::FULL);
             cp_async_wait_all();
             if (__syncthreads_and(mine)) {
                 T fr[RO][2], xr[RO][2];
                 W.template own<true>(fv, xv, fscale, fshift, (par0 + (threadIdx.x >> 5)) & 1, fr, xr);
-                up_open<T, TX, TF, TC, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, fr, xr, acc);
+                up_open<T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, fr, xr, acc);
                 done = true;
             } else {
-                W.template stash<true>(fv, xv, bits, fscale, fshift, par0);
+                if constexpr (FINE) W.template stash<true>(fv, xv, bits, fscale, fshift, par0);
+                else W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
             }
         } else {
             W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
             cp_async_wait_all();
         }
-    } else {
-        W.fill_tables(nullptr, L.dirichlet());
-        W.template load<true>(L, xin, fin, fscale, fshift, wj0, wi0, par0);
-        cp_async_wait_all();
     }
     if (!done) {
         __syncthreads();
