@@ -108,6 +108,7 @@ struct Multigrid {
     int which = 0;
     FineView fine{};
     uint8_t *nb = nullptr;            // fine bits, (n2,n1)
+    uint8_t *cg_open = nullptr;       // per tile of k_cg_dir_apply: all unknowns, no wrap (mg.cu)
     std::vector<Level> lev;           // lev[0] unused except sizes; lev[l>=1] coarse
     std::vector<Level> glev;          // slab mode: global (replicated) copies of the tail levels
     int gs = 0, gn = 0;               // ghost rows south / north of the owned rows, every level

@@ -309,11 +309,28 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
 //   A CTA forms pnew once per point of a (64+2) x (16+2) window in shared
 //   memory and applies the 5-point operator from there.
 constexpr int CGX = 64, CGY = 16;
+
+// the two expressions both paths of k_cg_dir_apply evaluate, with explicit roundings
+__device__ __forceinline__ double cg_pnew(double z, double mz, double beta, double pold) {
+    return __fma_rn(beta, pold, __dsub_rn(z, mz));
+}
+__device__ __forceinline__ double cg_q(const FineView &F, double diag, double pc, double w, double e, double s, double n) {
+    return __fma_rn(diag, pc, -__fma_rn(F.cx, __dadd_rn(w, e), __dmul_rn(F.cy, __dadd_rn(s, n))));
+}
+__device__ __forceinline__ double cg_diag(const FineView &F, double cw, double ce, double cs, double cn) {
+    return F.dirichlet ? __fma_rn(2.0, __dadd_rn(F.cx, F.cy), F.shift)
+                       : __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(cw, ce), cs), cn), F.shift);
+}
+
+//   tile_open[tile] != 0 (k_cg_tile_flags): the whole window lies inside the array, needs
+//   no periodic wrap and holds unknowns only -> no mask bytes, no bounds tests, and the
+//   loads do not wait for a mask byte first.  Same arithmetic, same bits.
 template <typename TZ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ pold,
                double *__restrict__ pnew, double *__restrict__ q, double *__restrict__ scal, int it,
-               int singular, double inv_n, double *part, unsigned int *count) {
+               int singular, double inv_n, double *part, unsigned int *count,
+               const uint8_t *__restrict__ tile_open) {
     __shared__ double sp[CGY + 2][CGX + 2];
     double rznew = scal[S_RZNEW];
     double mz = singular ? scal[S_SUMZ] * inv_n : 0.0;
@@ -321,10 +338,45 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ 
     if (it > 0) { double rzold = scal[S_RZ0 + ((it - 1) & 1)]; beta = rzold != 0.0 ? rznew / rzold : 0.0; }
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY;
+    const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
     double v[1] = {0.0};
     for (int tile = blockIdx.y * gridDim.x + blockIdx.x; tile < ntx * nty; tile += gridDim.x * gridDim.y) {
         const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
+        const bool open = tile_open != nullptr && tile_open[tile];     // block-uniform
         __syncthreads();
+        if (open) {
+            const long base = (long)(F.oj + j0 - 1) * F.n1 + F.oi + i0 - 1;
+            constexpr int NW = ((CGY + 2) * (CGX + 2) + 255) / 256;
+            TZ zv[NW];
+            double pv[NW];
+#pragma unroll
+            for (int u = 0; u < NW; u++) {      // every load first
+                int t = tid + u * 256;
+                int a = t / (CGX + 2), b = t - a * (CGX + 2);
+                bool in = t < (CGY + 2) * (CGX + 2);
+                long idx = base + (long)a * F.n1 + b;
+                zv[u] = in ? z[idx] : TZ(0);
+                pv[u] = in ? pold[idx] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < NW; u++) {
+                int t = tid + u * 256;
+                if (t < (CGY + 2) * (CGX + 2)) (&sp[0][0])[t] = cg_pnew((double)zv[u], mz, beta, pv[u]);
+            }
+            __syncthreads();
+            const long idx0 = base + (long)(1 + threadIdx.y) * F.n1 + 1 + threadIdx.x;
+#pragma unroll
+            for (int r = 0; r < CGY / 4; r++) {
+                const int a = 1 + threadIdx.y + 4 * r, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * r;
+                const long idx = idx0 + (long)(4 * r) * F.n1;
+                double pc = sp[a][b];
+                double qv = cg_q(F, diag_open, pc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
+                pnew[idx] = pc;
+                q[idx] = qv;
+                if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
+            }
+            continue;
+        }
         for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
             int j = j0 - 1 + a, i = i0 - 1 + b;
@@ -332,7 +384,7 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ 
             double pv = 0.0;
             long idx;
             if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF))
-                pv = ((double)z[idx] - mz) + beta * pold[idx];
+                pv = cg_pnew((double)z[idx], mz, beta, pold[idx]);
             sp[a][b] = pv;
         }
         __syncthreads();
@@ -346,17 +398,35 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ 
             if (!(c & NB_SELF)) continue;
             double cw = (c & NB_W) ? F.cx : 0.0, ce = (c & NB_E) ? F.cx : 0.0;
             double cs = (c & NB_S) ? F.cy : 0.0, cn = (c & NB_N) ? F.cy : 0.0;
-            double diag = F.dirichlet ? (2.0 * (F.cx + F.cy) + F.shift) : (((cw + ce) + cs) + cn + F.shift);
+            double diag = cg_diag(F, cw, ce, cs, cn);
             double pc = sp[a][b];
             // closed faces lead to points that are not unknowns: their sp entry is 0
-            double qv = diag * pc - (F.cx * (sp[a][b - 1] + sp[a][b + 1]) + F.cy * (sp[a - 1][b] + sp[a + 1][b]));
+            double qv = cg_q(F, diag, pc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
             pnew[idx] = pc;
             q[idx] = qv;
-            if (j >= F.jo0 && j < F.jo1) v[0] += pc * qv;
+            if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
         }
     }
     grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) scal[S_RZ0 + (it & 1)] = rznew;
+}
+
+// which tiles of k_cg_dir_apply are open: one CTA per tile
+__global__ void __launch_bounds__(256) k_cg_tile_flags(FineView F, uint8_t *__restrict__ flags) {
+    const int ntx = (F.nx + CGX - 1) / CGX;
+    const int tile = blockIdx.x;
+    const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
+    int good = j0 - 1 >= 0 && j0 + CGY + 1 <= F.ny && i0 - 1 >= 0 && i0 + CGX + 1 <= F.nx &&
+               F.oj + j0 - 1 >= 0 && F.oj + j0 + CGY + 1 <= F.n2 && F.oi + i0 - 1 >= 0 && F.oi + i0 + CGX + 1 <= F.n1;
+    if (good) {
+        const long base = (long)(F.oj + j0 - 1) * F.n1 + F.oi + i0 - 1;
+        for (int t = threadIdx.x; t < (CGY + 2) * (CGX + 2); t += blockDim.x) {
+            int a = t / (CGX + 2), b = t - a * (CGX + 2);
+            if ((F.nb[base + (long)a * F.n1 + b] & 31) != 31) good = 0;    // an unknown with four open faces
+        }
+    }
+    good = __syncthreads_and(good);
+    if (threadIdx.x == 0) flags[tile] = (uint8_t)good;
 }
 
 // y = A x = -L x on the unknowns, 0 elsewhere inside the window
@@ -687,6 +757,7 @@ void mg_free(f2d_ctx *c, int which) {
     Multigrid &M = c->mg[which];
     for (cudaGraphExec_t &g : M.gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     cudaFree(M.nb);
+    cudaFree(M.cg_open); M.cg_open = nullptr;
     for (double *p : {M.r, M.z, M.p, M.q, M.p2}) cudaFree(p);
     cudaFree(M.zf);
     cudaFree(M.zf2);
@@ -809,6 +880,11 @@ int mg_build(f2d_ctx *c, int which) {
     F.nb = M.nb;
     k_build_nb<<<grd(n1, n2), blk(), 0, c->stream>>>(F, sm, M.nb);
     LAUNCH_CHECK(c);
+    {   // open tiles of k_cg_dir_apply
+        const int ntiles = ((F.nx + CGX - 1) / CGX) * ((F.ny + CGY - 1) / CGY);
+        F2D_CUDA(cudaMalloc(&M.cg_open, std::max(ntiles, 1)));
+        if (ntiles > 0) { k_cg_tile_flags<<<ntiles, 256, 0, c->stream>>>(F, M.cg_open); LAUNCH_CHECK(c); }
+    }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(sm);
 
@@ -972,6 +1048,11 @@ static int mg_build_slab(f2d_ctx *c, int which) {
     F.nb = M.nb;
     k_build_nb<<<grd(n1, n2), blk(), 0, c->stream>>>(F, sm, M.nb);
     LAUNCH_CHECK(c);
+    {   // open tiles of k_cg_dir_apply
+        const int ntiles = ((F.nx + CGX - 1) / CGX) * ((F.ny + CGY - 1) / CGY);
+        F2D_CUDA(cudaMalloc(&M.cg_open, std::max(ntiles, 1)));
+        if (ntiles > 0) { k_cg_tile_flags<<<ntiles, 256, 0, c->stream>>>(F, M.cg_open); LAUNCH_CHECK(c); }
+    }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(sm);
     if (M.n_global == 0) { M.built = true; return F2D_OK; }
@@ -1259,6 +1340,17 @@ static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, i
 // where the finished correction of coarse level l lives: the tail kernel works
 // in place, the tile kernels write their up leg to the second buffer
 static const CT *level_result(const Multigrid &M, int l) { return l >= M.tail ? M.lev[l].x : M.lev[l].x2; }
+
+// persistent grid of k_cg_dir_apply: exactly the CTAs that are resident at once
+template <typename TZ>
+static dim3 dir_apply_grid(const f2d_ctx *c) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_dir_apply<TZ>, 256, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+    }
+    return dim3(c->nsm * per_sm);
+}
 
 // F2D_NO_OPEN=1: every tile takes the generic (masked) path -- A/B timing and the
 // test that both paths give the same bits
@@ -1554,6 +1646,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const int maxit = c->cfg.solver_maxit > 0 ? c->cfg.solver_maxit : 100;
     const double fscale = -bscale;   // L = -A
     const dim3 nblk = cg_grid(c, F);
+    const uint8_t *cg_open = allow_open_tiles() ? M.cg_open : nullptr;
     const bool singular = !F.dirichlet && F.shift == 0.0;
     const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
     const double N = M.n_global, inv_n = 1.0 / N;
@@ -1609,12 +1702,12 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 F2D_TRY(vcycle_unfused(c, M, M.z, M.r, 1.0, true));
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
-                k_cg_dir_apply<double><<<nblk, dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
-                                                             c->d_part, c->d_count);
+                k_cg_dir_apply<double><<<dir_apply_grid<double>(c), dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
+                                                             c->d_part, c->d_count, cg_open);
             } else {
                 F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
-                k_cg_dir_apply<float><<<nblk, dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
-                                                            c->d_part, c->d_count);
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, singular ? 1 : 0, inv_n,
+                                                            c->d_part, c->d_count, cg_open);
             }
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
@@ -1746,7 +1839,8 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 *bytes = npts * (1.5 * 8 + 0.5);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.dir_apply") {
-                k_cg_dir_apply<float><<<nblk, dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count);
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count,
+                                                                            allow_open_tiles() ? M.cg_open : nullptr);
                 *bytes = npts * (4 + 3 * 8 + 1);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.update") {
