@@ -1394,6 +1394,10 @@ static int launch_up0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const d
                                                UpArgs{C.ny, C.nx, C.pitch, F.periodic, allow_open_tiles()},
                                                level_result(M, 1), c->d_part, c->d_count, c->d_scal + S_RZNEW);
     LAUNCH_CHECK(c);
+    if (DOT) {
+        k_fold_partials<OpSum, 2><<<1, 1024, 0, c->stream>>>(c->d_part, g.x * g.y, c->d_scal + S_RZNEW);
+        LAUNCH_CHECK(c);
+    }
     return F2D_OK;
 }
 

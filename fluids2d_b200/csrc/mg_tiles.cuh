@@ -928,7 +928,7 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
         __syncthreads();
         up_body<T, TX, TF, TC, FINE, DOT, NU, WJ>(W, L, XC, xout, fin, fscale, fshift, tj0, ti0, acc);
     }
-    if (DOT) grid_reduce<OpSum, 2>(acc, part, count, out);
+    if (DOT) block_partials<OpSum, 2>(acc, part);     // folded by k_fold_partials (launch_up0)
 }
 
 }  // namespace f2d

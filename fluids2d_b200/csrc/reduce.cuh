@@ -47,6 +47,36 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV]) {
     __syncthreads();
 }
 
+// Two-kernel variant for kernels whose CTAs are short-lived (one tile each): the
+// CTA only stores its partial and leaves -- no fence, no atomic round trip, no
+// second barrier while it holds its slot -- and k_fold_partials, launched right
+// behind it, folds the partials in a fixed order.
+template <class Op, int NV>
+__device__ __forceinline__ void block_partials(double (&v)[NV], double *part) {
+    block_reduce<Op, NV>(v);
+    if (threadIdx.y * blockDim.x + threadIdx.x == 0) {
+        unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int k = 0; k < NV; k++) part[(size_t)k * nblocks + bid] = v[k];
+    }
+}
+
+template <class Op, int NV>
+__global__ void __launch_bounds__(1024) k_fold_partials(const double *__restrict__ part, unsigned nblocks, double *out) {
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        acc[k] = Op::id();
+        for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x)
+            acc[k] = Op::ap(acc[k], part[(size_t)k * nblocks + b]);
+    }
+    block_reduce<Op, NV>(acc);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) out[k] = acc[k];
+    }
+}
+
 // Grid-wide: every block calls this with its per-thread values.  `part` holds
 // NV * nblocks doubles, `count` one zero-initialised counter (reset on exit),
 // `out[k]` receives the result.  nblocks = gridDim.x*gridDim.y.
