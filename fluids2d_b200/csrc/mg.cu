@@ -1829,11 +1829,13 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 F2D_TRY((launch_up0<float, 2, true>(c, M, M.zf, M.zf2, M.r, 1.0, -1)));
                 *bytes = npts * (4 + 8 + 1 + 1 + 4);
             } else if (k == "mg.down1") {
+                // open tiles (regular coefficients) do not read cx, cy, dinv: R b code, W x + b2 (1/4)
                 F2D_TRY((coarse_down<2>(c, M, 1)));
-                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (4 * 4 + 1 + 4 + 1);
+                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (allow_open_tiles() ? (4 + 1 + 4 + 1) : (4 * 4 + 1 + 4 + 1));
             } else if (k == "mg.up1") {
+                // R x b code + x2 of level 2 (1/4), W x2
                 F2D_TRY((coarse_up<2>(c, M, 1)));
-                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (5 * 4 + 1 + 1 + 4);
+                *bytes = (double)M.lev[1].ny * M.lev[1].nx * (allow_open_tiles() ? (2 * 4 + 1 + 1 + 4) : (5 * 4 + 1 + 1 + 4));
             } else if (k == "mg.tail") {
                 F2D_TRY(launch_tail(c, M));
                 *bytes = 0;

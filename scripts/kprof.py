@@ -1,0 +1,28 @@
+"""one launch of each hot kernel inside an NVTX range, for
+ncu --set full --nvtx --nvtx-include "f2dprof/" python scripts/kprof.py [names...]"""
+import sys
+sys.path.insert(0, ".")
+import torch
+import bench
+import fluids2d_b200 as f2d
+
+f2d.Param._quiet = True
+p = bench.param_for(4096, f2d.Param)
+m = f2d.Model(p)
+s = m.state
+s.omega[...] = bench.turbulence_vorticity(m.mesh.x("v"), m.mesh.y("v"), m.mesh.area)
+s.omega[...] *= m.mesh.mskv
+f2d.tools.set_uv_from_omega(m, s.omega, s.u)
+m.integrator.diag(s)
+m.integrator.upload(s)
+e = m.mesh.engine
+e.step(1e-4, 2)
+names = sys.argv[1:] or e.bench_kernel_names()
+for k in names:
+    e.bench_kernel(k, 3)          # warm
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("f2dprof")
+for k in names:
+    e.bench_kernel(k, 1)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
