@@ -1206,124 +1206,17 @@ __device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const TailSm &S, 
     return S.cx[s] * S.x[w] + S.cx[e] * S.x[e] + S.cy[s] * S.x[s - L.sp] + S.cy[s + L.sp] * S.x[s + L.sp];
 }
 
-// The phases of the tail V-cycle, written once for two scopes:
-//   WARP = false: the whole CTA works on the level, phases end in __syncthreads()
-//   WARP = true : warp 0 alone (levels of <= 64 points: one or two points per
-//                 lane), phases end in __syncwarp() -- on a 4096^2 grid 44 of
-//                 the 81 phases of the tail are on the 8x8 and 4x4 levels, where
-//                 a block-wide barrier and 31 idle warps cost far more than the work
-template <bool WARP>
-__device__ __forceinline__ void tail_sync() {
-    if (WARP) __syncwarp();
-    else __syncthreads();
-}
-template <bool WARP, class F>
-__device__ __forceinline__ void tail_for(const TailLevel &L, F f) {
-    if (WARP) {
-        const int n = L.ny * L.nx;
-        for (int p = threadIdx.x & 31; p < n; p += 32) {
-            int J = p / L.nx;
-            f(J, p - J * L.nx);
-        }
-    } else {
-        for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
-            for (int I = threadIdx.x & 31; I < L.nx; I += 32) f(J, I);
-    }
-}
-template <bool WARP>
-__device__ __forceinline__ void tail_zero(const TailLevel &L, CT *x) {
-    const int n = (L.ny + 2) * L.sp;
-    for (int t = WARP ? (threadIdx.x & 31) : threadIdx.x; t < n; t += WARP ? 32 : blockDim.x) x[t] = CT(0);
-    tail_sync<WARP>();
-}
-
-template <bool WARP>
 __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
     TailSm S = tail_sm(sm, L);
-    auto point = [&](int J, int I) {
-        int s = (J + 1) * L.sp + I + 1;
-        CT di = S.dinv[s];
-        CT a = zero ? CT(0) : tail_offdiag(L, S, periodic, J, I);
-        S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
-    };
-    if (WARP) {
-        tail_for<true>(L, [&](int J, int I) { if (((J + I) & 1) == color) point(J, I); });
-    } else {
-        // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
-        for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
-            for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) point(J, I);
-    }
-    tail_sync<WARP>();
-}
-
-// nu1 sweeps from zero, residual, restriction to the next level's right-hand side
-template <bool WARP>
-__device__ __forceinline__ void tail_down(const TailLevel &L, const TailLevel &C, CT *sm, int per, int nu1) {
-    TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
-    tail_zero<WARP>(L, S.x);
-    for (int s = 0; s < nu1; s++) {
-        tail_relax<WARP>(L, sm, per, 0, s == 0);
-        tail_relax<WARP>(L, sm, per, 1, false);
-    }
-    tail_for<WARP>(L, [&](int J, int I) {   // residual / prolongation normaliser
-        int sidx = (J + 1) * L.sp + I + 1;
-        CT di = S.dinv[sidx], res = CT(0);
-        if (di != CT(0)) {
-            CT a = tail_offdiag(L, S, per, J, I);
-            res = (S.b[sidx] - (S.x[sidx] / di - a)) / S.w[sidx];
+    // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
+    for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
+        for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) {
+            int s = (J + 1) * L.sp + I + 1;
+            CT di = S.dinv[s];
+            CT a = zero ? CT(0) : tail_offdiag(L, S, periodic, J, I);
+            S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
         }
-        S.r[sidx] = res;
-    });
-    tail_sync<WARP>();
-    tail_for<WARP>(C, [&](int J, int I) {   // restriction R = P^T
-        CT acc = CT(0);
-#pragma unroll
-        for (int a = -1; a <= 2; a++) {
-            int j = 2 * J + a;
-            if (j < 0 || j >= L.ny) continue;
-            CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
-#pragma unroll
-            for (int b = -1; b <= 2; b++) {
-                int i = 2 * I + b;
-                if (per) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
-                if (i < 0 || i >= L.nx) continue;
-                CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
-                acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
-            }
-        }
-        SC.b[(J + 1) * C.sp + I + 1] = acc;
-    });
-    tail_sync<WARP>();
-}
-
-// coarsest level: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
-template <bool WARP>
-__device__ __forceinline__ void tail_coarsest(const TailLevel &L, CT *sm, int per, int nsw) {
-    TailSm S = tail_sm(sm, L);
-    tail_zero<WARP>(L, S.x);
-    for (int s = 0; s < 4 * nsw; s++)
-        tail_relax<WARP>(L, sm, per, (s < 2 * nsw) ? (s & 1) : 1 - (s & 1), s == 0);
-}
-
-// prolongation of the next level's correction, nu2 sweeps (B,R)
-template <bool WARP>
-__device__ __forceinline__ void tail_up(const TailLevel &L, const TailLevel &C, CT *sm, int per, int nu2) {
-    TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
-    tail_for<WARP>(L, [&](int J, int I) {
-        int sidx = (J + 1) * L.sp + I + 1;
-        if (S.dinv[sidx] == CT(0)) return;        // not an unknown (set-up clears the code where 1/diag is 0)
-        int J0, Jn, I0, In;
-        parents(J, I, J0, Jn, I0, In);
-        if (per) In = wrap_mod(In, C.nx);
-        int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
-        CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
-        S.x[sidx] += v / S.w[sidx];
-    });
-    tail_sync<WARP>();
-    for (int s = 0; s < nu2; s++) {
-        tail_relax<WARP>(L, sm, per, 1, false);
-        tail_relax<WARP>(L, sm, per, 0, false);
-    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailArgs Ain) {
@@ -1354,25 +1247,72 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
         }
     }
     __syncthreads();
-    // levels [ls, nlev) have at most 64 points each: warp 0 runs their whole
-    // sub-V-cycle on its own (only when the coarsest level is that small)
-    const int last = A.nlev - 1;
-    int ls = A.nlev;
-    if (A.lev[last].ny * A.lev[last].nx <= 64)
-        for (ls = last; ls > 0 && A.lev[ls - 1].ny * A.lev[ls - 1].nx <= 64; ls--) {}
-    const int nblock = ls < A.nlev ? ls : last;      // levels the whole CTA relaxes on the way down
-    for (int l = 0; l < nblock; l++) tail_down<false>(A.lev[l], A.lev[l + 1], sm, per, A.nu1);
-    if (ls < A.nlev) {
-        if ((threadIdx.x >> 5) == 0) {
-            for (int l = ls; l < last; l++) tail_down<true>(A.lev[l], A.lev[l + 1], sm, per, A.nu1);
-            tail_coarsest<true>(A.lev[last], sm, per, A.nsw);
-            for (int l = last - 1; l >= ls; l--) tail_up<true>(A.lev[l], A.lev[l + 1], sm, per, A.nu2);
+    for (int l = 0; l < A.nlev - 1; l++) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
+        __syncthreads();
+        for (int s = 0; s < A.nu1; s++) {
+            tail_relax(L, sm, per, 0, s == 0);
+            tail_relax(L, sm, per, 1, false);
+        }
+        TAIL_LOOP(L) {   // residual / prolongation normaliser
+            int sidx = (J + 1) * L.sp + I + 1;
+            CT di = S.dinv[sidx], res = CT(0);
+            if (di != CT(0)) {
+                CT a = tail_offdiag(L, S, per, J, I);
+                res = (S.b[sidx] - (S.x[sidx] / di - a)) / S.w[sidx];
+            }
+            S.r[sidx] = res;
         }
         __syncthreads();
-    } else {
-        tail_coarsest<false>(A.lev[last], sm, per, A.nsw);
+        TAIL_LOOP(C) {   // restriction R = P^T
+            CT acc = CT(0);
+#pragma unroll
+            for (int a = -1; a <= 2; a++) {
+                int j = 2 * J + a;
+                if (j < 0 || j >= L.ny) continue;
+                CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
+#pragma unroll
+                for (int b = -1; b <= 2; b++) {
+                    int i = 2 * I + b;
+                    if (per) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
+                    if (i < 0 || i >= L.nx) continue;
+                    CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
+                    acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
+                }
+            }
+            SC.b[(J + 1) * C.sp + I + 1] = acc;
+        }
+        __syncthreads();
     }
-    for (int l = nblock - 1; l >= 0; l--) tail_up<false>(A.lev[l], A.lev[l + 1], sm, per, A.nu2);
+    {   // coarsest: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
+        const TailLevel &L = A.lev[A.nlev - 1];
+        TailSm S = tail_sm(sm, L);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
+        __syncthreads();
+        for (int s = 0; s < 4 * A.nsw; s++)
+            tail_relax(L, sm, per, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
+    }
+    for (int l = A.nlev - 2; l >= 0; l--) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        TAIL_LOOP(L) {
+            int sidx = (J + 1) * L.sp + I + 1;
+            if (S.dinv[sidx] == CT(0)) continue;      // not an unknown (set-up clears the code where 1/diag is 0)
+            int J0, Jn, I0, In;
+            parents(J, I, J0, Jn, I0, In);
+            if (per) In = wrap_mod(In, C.nx);
+            int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
+            CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
+            S.x[sidx] += v / S.w[sidx];
+        }
+        __syncthreads();
+        for (int s = 0; s < A.nu2; s++) {
+            tail_relax(L, sm, per, 1, false);
+            tail_relax(L, sm, per, 0, false);
+        }
+    }
     {   // the correction of the first tail level goes back to global memory
         const TailLevel &L = A.lev[0];
         TailSm S = tail_sm(sm, L);
