@@ -809,7 +809,7 @@ static int choose_tail(std::vector<Level> &lev, int first_allowed, int &tail) {
         if ((long)lev[l].ny * lev[l].nx <= 4096 && n - l <= 16) tail = l;
     auto need = [&](int from) {
         size_t b = 0;
-        for (int l = from; l < n; l++) b += (size_t)3 * (lev[l].ny + 2) * (lev[l].nx + 2) * sizeof(CT);
+        for (int l = from; l < n; l++) b += (size_t)TAIL_ARRAYS * (lev[l].ny + 2) * (lev[l].nx + 2) * sizeof(CT);
         return b;
     };
     while (tail < n - 1 && need(tail) > 200 * 1024) tail++;
@@ -925,8 +925,11 @@ int mg_build(f2d_ctx *c, int which) {
     M.lev[0].ny = F.ny; M.lev[0].nx = F.nx;
     // levels from M.tail on are small enough for the single-CTA tail kernel
     M.tail = (int)M.lev.size() - 1;
+    // measured at 4096^2 (ms per step): tail from 64^2 down 11.20, from 32^2 10.98, from 16^2 10.96 --
+    // a handful of tile CTAs relax a 64^2 level faster than one CTA does between block-wide barriers
+    static const long tail_points = getenv("F2D_TAIL_POINTS") ? atol(getenv("F2D_TAIL_POINTS")) : 1024;
     for (int l = (int)M.lev.size() - 1; l >= 1; l--)
-        if ((long)M.lev[l].ny * M.lev[l].nx <= 4096 && (int)M.lev.size() - l <= 16) M.tail = l;
+        if ((long)M.lev[l].ny * M.lev[l].nx <= tail_points && (int)M.lev.size() - l <= 16) M.tail = l;
     {   // x, b, r and the coefficient copies of every tail level must fit in shared memory
         auto need = [&](int from) {
             size_t b = 0;
@@ -1167,7 +1170,7 @@ static int mg_build_slab(f2d_ctx *c, int which) {
 
 // ---------------------------------------------------------------------------
 // single-CTA tail: the whole sub-V-cycle of the levels whose grids are small
-// (<= 4096 points) in one launch.  Everything lives in shared memory: x, b and
+// (<= 1024 points on one GPU, <= 4096 gathered points in slab mode) in one launch.  Everything lives in shared memory: x, b and
 // the residual of every tail level, and a copy of the coefficients (couplings,
 // inverse diagonal, prolongation normaliser) made once at the start with all
 // loads in flight -- the kernel is a chain of ~80 short phases separated by
