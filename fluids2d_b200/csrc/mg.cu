@@ -1439,13 +1439,18 @@ static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     return F2D_OK;
 }
 
+// rows from which a coarse level gets 64-row windows instead of 32-row ones
+static int tall_window_rows() {
+    static const int v = getenv("F2D_WJ_SWITCH") ? atoi(getenv("F2D_WJ_SWITCH")) : 1024;   // experiments
+    return v;
+}
 template <int NU>
 static int coarse_down(f2d_ctx *c, Multigrid &M, int l) {
-    return M.lev[l].ny >= 1024 ? launch_down<NU, 64>(c, M, l) : launch_down<NU, 32>(c, M, l);
+    return M.lev[l].ny >= tall_window_rows() ? launch_down<NU, 64>(c, M, l) : launch_down<NU, 32>(c, M, l);
 }
 template <int NU>
 static int coarse_up(f2d_ctx *c, Multigrid &M, int l) {
-    return M.lev[l].ny >= 1024 ? launch_up<NU, 64>(c, M, l) : launch_up<NU, 32>(c, M, l);
+    return M.lev[l].ny >= tall_window_rows() ? launch_up<NU, 64>(c, M, l) : launch_up<NU, 32>(c, M, l);
 }
 
 #define NU_SWITCH(nu, CALL)                                   \

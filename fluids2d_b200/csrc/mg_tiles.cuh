@@ -47,6 +47,10 @@ constexpr int TW = 64;    // window width in points
 constexpr int TK = 32;    // points of one colour per window row
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
+// resident CTAs per SM the fp32 fine-level legs are compiled for (3 -> 40 registers)
+#ifndef F2D_FINE_CTAS
+#define F2D_FINE_CTAS 3
+#endif
 
 __host__ __device__ constexpr int halo_down(int nu, bool zero) { return zero ? 2 * nu + 1 : 2 * nu + 2; }
 __host__ __device__ constexpr int halo_up(int nu) { return 2 * nu; }
@@ -655,7 +659,7 @@ __device__ __forceinline__ void down_open(Window<T, FINE, WJ> &W, const Lev &L, 
 }
 
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool ZERO, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
+__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? F2D_FINE_CTAS : 2)
 k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
           const double *__restrict__ scal, int sumr_slot, double inv_n, DownArgs A, TC *__restrict__ bc) {
     constexpr int H = halo_down(NU, ZERO);
@@ -851,7 +855,7 @@ __device__ __forceinline__ void up_open(Window<T, FINE, WJ> &W, const Lev &L, co
 }
 
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
-__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? 3 : 2)
+__global__ void __launch_bounds__(TILE_THREADS, (FINE && sizeof(T) == 4) ? F2D_FINE_CTAS : 2)
 k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__restrict__ fin, double fscale,
         const double *__restrict__ scal, int sumr_slot, double inv_n, UpArgs A, const TC *__restrict__ xc,
         double *part, unsigned int *count, double *out) {
