@@ -11,56 +11,43 @@ _integrators = ["rk3", "ef", "enrk3", "LFRA"]
 DEVICE_MODELS = ["euler", "boussinesq", "rsw", "qgrsw", "eulerpsi", "qg", "advection", "vectoradv"]
 
 
+# name -> default, grouped as in the reference's constructor (param.py:13-59)
+_REFERENCE_DEFAULTS = dict(
+    # which equations, on which grid
+    model="euler", nx=40, ny=40, Lx=1.0, Ly=1.0,
+    xperiodic=False, yperiodic=False, halowidth=3, noslip=None,
+    # physical constants of the rotating / stratified models
+    f0=10.0, beta=0.0, g=1, H=1,
+    # length of the run and step control
+    tend=1.0, dt=0.0, maxite=100, dtmax=9e99, integrator="rk3", cfl=0.9, RAgamma=0.1,
+    # observation points: print, plot, history file
+    nprint=1, nplot=5, animation=False, generate_mp4=False, plotvar=None, clims=None,
+    cmap="RdBu_r", outputfile="history.nc", var_to_store=[], nhis=0,
+    # numerics of the three advective operators
+    compflux="weno", vortexforce="weno", innerproduct="weno", maxorder=6,
+    tracer=None, nthreads=1,
+)
+
+# NEW: device / elliptic-solver controls (the reference has a direct solve)
+_DEVICE_DEFAULTS = dict(
+    device=0,
+    rank=0, nranks=1,       # y-slab decomposition: this process's slab out of nranks (slabs.py)
+    solver="pcg",           # "pcg": multigrid-preconditioned CG; "mg": plain V-cycles
+    solver_rtol=1e-12,      # ||b - A x|| <= rtol ||b||
+    solver_maxit=100,
+    solver_nu=2,            # red-black sweeps before and after each coarse correction
+    solver_guess=4,         # first guess from the same RK stage of earlier steps: 0 off,
+                            # 1 previous, 2 linear, 3 quadratic, 4 cubic extrapolation (max 6)
+)
+
+
 class Param:
     _quiet = False      # set Param._quiet = True to silence the help banner
 
     def __init__(self):
-        self.model = "euler"
-        self.nx = 40
-        self.ny = 40
-        self.Lx = 1.0
-        self.Ly = 1.0
-        self.xperiodic = False
-        self.yperiodic = False
-        self.halowidth = 3
-        self.noslip = None
-        self.f0 = 10.0
-        self.beta = 0.0
-        self.g = 1
-        self.H = 1
-        self.tend = 1.0
-        self.dt = 0.0
-        self.maxite = 100
-        self.dtmax = 9e99
-        self.nprint = 1
-        self.nplot = 5
-        self.animation = False
-        self.generate_mp4 = False
-        self.plotvar = None
-        self.clims = None
-        self.cmap = "RdBu_r"
-        self.outputfile = "history.nc"
-        self.var_to_store = []
-        self.nhis = 0
-        self.integrator = "rk3"
-        self.cfl = 0.9
-        self.RAgamma = 0.1
-        self.compflux = "weno"
-        self.vortexforce = "weno"
-        self.innerproduct = "weno"
-        self.maxorder = 6
-        self.tracer = None
-        self.nthreads = 1
-        # NEW: device / elliptic-solver controls (the reference has a direct solve)
-        self.device = 0
-        self.rank = 0                # y-slab decomposition: this process's slab ...
-        self.nranks = 1              # ... out of nranks (one GPU each); see slabs.py
-        self.solver = "pcg"          # "pcg": multigrid-preconditioned CG; "mg": plain V-cycles
-        self.solver_rtol = 1e-12     # ||b - A x|| <= rtol ||b||
-        self.solver_maxit = 100
-        self.solver_nu = 2           # red-black sweeps before and after each coarse correction
-        self.solver_guess = 4        # first guess from the same RK stage of earlier steps: 0 off,
-                                     # 1 previous, 2 linear, 3 quadratic, 4 cubic extrapolation (max 6)
+        for group in (_REFERENCE_DEFAULTS, _DEVICE_DEFAULTS):
+            for name, value in group.items():
+                setattr(self, name, list(value) if isinstance(value, list) else value)
         self.__parameters__ = _public_names(self)
         self.help()
 
