@@ -137,3 +137,35 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle harness", ""), os.path.join(dirpath, f)
+
+
+def test_argument_errors_are_status_codes_not_crashes(built):
+    """Bad arguments come back as F2D_ERR_ARG with a message in f2d_last_error();
+    the checks sit in front of every CUDA call, so this runs without a device
+    (int status, no exceptions across the boundary)."""
+    from fluids2d_b200 import _cabi
+    ERR_ARG = -2
+    for path in built:
+        lib = ctypes.CDLL(path)
+        lib.f2d_last_error.restype = ctypes.c_char_p
+        ctx = ctypes.c_void_p()
+        assert lib.f2d_create(None, ctypes.byref(ctx)) == ERR_ARG
+        cfg = _cabi.Config()
+        cfg.nx, cfg.ny, cfg.nh, cfg.maxorder = 40, 40, 3, 6
+        bad = [("nx", 0, b"positive"), ("nh", 2, b"halowidth"), ("model", 99, b"model"),
+               ("integrator", 7, b"integrator"), ("maxorder", 5, b"maxorder"),
+               ("vortexforce", 4, b"vortexforce"), ("innerproduct", 5, b"innerproduct")]
+        for field, value, word in bad:
+            c2 = _cabi.Config.from_buffer_copy(cfg)
+            setattr(c2, field, value)
+            assert lib.f2d_create(ctypes.byref(c2), ctypes.byref(ctx)) == ERR_ARG, field
+            assert word in lib.f2d_last_error(), (field, lib.f2d_last_error())
+            assert not ctx.value
+        # null context / null pointers
+        buf = (ctypes.c_double * 4)()
+        assert lib.f2d_upload(None, b"u.x", buf) == ERR_ARG
+        assert lib.f2d_download(None, b"u.x", buf) == ERR_ARG
+        assert lib.f2d_step(None, ctypes.c_double(0.1), 1) == ERR_ARG
+        assert lib.f2d_solve(None, 0, None, ctypes.c_double(1.0), None, None, None) == ERR_ARG
+        assert lib.f2d_max_abs_U(None, None) == ERR_ARG
+        assert lib.f2d_device_count(None) == ERR_ARG
