@@ -169,3 +169,26 @@ def test_argument_errors_are_status_codes_not_crashes(built):
         assert lib.f2d_solve(None, 0, None, ctypes.c_double(1.0), None, None, None) == ERR_ARG
         assert lib.f2d_max_abs_U(None, None) == ERR_ARG
         assert lib.f2d_device_count(None) == ERR_ARG
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/f2d.h is a C header (no C++ or torch types): a C99 program that
+    includes it compiles with -pedantic, links against libf2d.so and runs."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_f2d.c"
+    src.write_text('#include <stdio.h>\n#include "f2d.h"\n'
+                   "int main(void) {\n"
+                   "    f2d_ctx *ctx = 0;\n"
+                   "    int st = f2d_create(0, &ctx);   /* NULL config: F2D_ERR_ARG, no CUDA call */\n"
+                   '    printf("%d %d %s\\n", f2d_version(), st, f2d_last_error());\n'
+                   "    return st == F2D_ERR_ARG ? 0 : 1;\n}\n")
+    libdir = os.path.dirname(built[0])
+    exe = tmp_path / "use_f2d"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                    "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libf2d.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "100" and out[1] == "-2"
