@@ -192,3 +192,51 @@ def test_header_is_plain_c_and_links(built, tmp_path):
                     "-L", libdir, "-l:libf2d.so", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out[0] == "100" and out[1] == "-2"
+
+
+def _reference_module(name):
+    """load ONE host-only module of the live reference by path (no numba import);
+    in-container cross-check only -- the tree is absent on the GPU box"""
+    import importlib.util
+    path = f"/root/reference/src/fluids2d/{name}.py"
+    if not os.path.exists(path):
+        pytest.skip("live reference not present")
+    spec = importlib.util.spec_from_file_location(f"_ref_{name}", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.refcheck
+def test_param_defaults_equal_the_live_reference(capsys):
+    import fluids2d_b200 as f2d
+    from fluids2d_b200.param import _DEVICE_DEFAULTS
+    f2d.Param._quiet = True
+    mine, ref = f2d.Param(), _reference_module("param").Param()
+    capsys.readouterr()                       # the reference prints its help banner
+    ref_atts = {k: v for k, v in vars(ref).items() if "__" not in k}
+    my_atts = {k: v for k, v in vars(mine).items() if "__" not in k}
+    assert {k: my_atts[k] for k in ref_atts} == ref_atts
+    assert set(my_atts) - set(ref_atts) == set(_DEVICE_DEFAULTS)
+    assert f2d.Param().var_to_store is not mine.var_to_store     # no shared mutable default
+
+
+@pytest.mark.refcheck
+def test_clock_follows_the_live_reference(capsys):
+    import random
+    import fluids2d_b200 as f2d
+    from fluids2d_b200.timeline import Time
+    f2d.Param._quiet = True
+    p = f2d.Param()
+    p.tend, p.maxite, p.nhis, p.nplot, p.animation = 0.7, 60, 4, 3, True
+    mine, ref = Time(p), _reference_module("timeline").Time(p)
+    rng = random.Random(0)
+    while not ref.finished:
+        for attr in ("t", "ite", "finished", "update_anim", "save_to_file"):
+            assert getattr(mine, attr) == getattr(ref, attr), attr
+        mine.dt = ref.dt = rng.uniform(0.003, 0.03)      # adaptive step (model.py:71-87)
+        mine.pushforward()
+        ref.pushforward()
+    assert mine.finished and mine.t == ref.t and mine.tostring() == ref.tostring()
+    p.nhis, p.animation = 0, False
+    assert (mine.save_to_file, mine.update_anim) == (ref.save_to_file, ref.update_anim) == (False, False)
