@@ -74,6 +74,7 @@ SIGNATURES = {
     "f2d_solve": (_I, [_P, _I, _P, _D, _P, C.POINTER(_I), C.POINTER(_D)]),
     "f2d_apply_laplacian": (_I, [_P, _I, _P, _P]),
     "f2d_solver_stats": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_D)]),
+    "f2d_solver_info": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_D)]),
     "f2d_compflux": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I]),
     "f2d_vortexforce": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I]),
     "f2d_innerproduct": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I]),
@@ -234,10 +235,11 @@ class Engine:
         return out
 
     def set_topography(self, hb):
-        if hb is None or np.isscalar(hb):
-            assert not hb, "scalar topography other than 0 is not supported"
+        if hb is None or (np.isscalar(hb) and not hb):
             self._chk(self.lib.f2d_set_topography(self._h, None))
         else:
+            if np.isscalar(hb):            # a flat bottom at a non-zero level (qg_inversion uses hb * qgcoef)
+                hb = np.full(self.shape, float(hb))
             a = np.ascontiguousarray(hb, dtype=np.float64)
             assert a.shape == self.shape
             self._chk(self.lib.f2d_set_topography(self._h, _ptr(a)))
@@ -361,6 +363,12 @@ class Engine:
         self._chk(self.lib.f2d_solver_stats(self._h, C.byref(a), C.byref(b), C.byref(r)))
         return dict(nsolves=a.value, niters=b.value, max_relres=r.value)
 
+    def solver_info(self, which="c"):
+        """connected components / multigrid levels of a solver, worst right-hand-side incompatibility so far"""
+        nc, nl, inc = C.c_int(), C.c_int(), C.c_double()
+        self._chk(self.lib.f2d_solver_info(self._h, SOLVERS[which], C.byref(nc), C.byref(nl), C.byref(inc)))
+        return dict(components=nc.value, levels=nl.value, rhs_incompat=inc.value)
+
     # -- raw device memory (per-kernel tests, solves on host arrays) ----------
     def malloc(self, nbytes):
         p = C.c_void_p()
@@ -422,15 +430,26 @@ class Engine:
         self._chk(self.lib.f2d_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
-    BENCH_KERNELS = ("advection", "rk_update", "divergence", "project_diag", "mg.down0", "mg.up0",
-                     "mg.down1", "mg.up1", "mg.tail", "cg.dir_apply", "cg.update")
+    _MG_KERNELS = ("mg.down0", "mg.up0", "mg.down1", "mg.up1", "mg.tail", "cg.dir_apply", "cg.update")
+    BENCH_KERNELS = {
+        0: ("advection", "rk_update", "divergence", "project_diag") + _MG_KERNELS,                 # euler
+        1: ("advection", "flux_div", "rk_update", "divergence", "project_diag") + _MG_KERNELS,     # boussinesq
+        2: ("advection", "flux_div", "rk_update", "diag"),                                         # rsw: no solve in the step
+        3: ("advection", "flux_div", "qg_pv", "qg_back", "rk_update", "diag") + _MG_KERNELS,       # qgrsw
+    }
 
     def bench_kernel_names(self):
-        return list(self.BENCH_KERNELS)
+        """kernels f2d_bench_kernel can time alone for this model"""
+        return list(self.BENCH_KERNELS.get(self.cfg.model, ()))
 
-    def dominant_kernel(self):
-        """the kernel with the largest share of a step (profiles/): the fused fine-level up leg"""
-        return "mg.up0"
+    def launches_per_step(self, name, iters_per_solve):
+        """how often one RK3 step launches a benchmarked kernel (3 stages, one solve each)"""
+        if name.startswith(("mg.", "cg.")):
+            return 3.0 * iters_per_solve
+        if name == "rk_update":
+            # the projecting models fuse the velocity update into the tendency kernel
+            return {0: 0, 1: 3, 2: 9, 3: 9}[self.cfg.model]
+        return 3.0
 
     def bench_kernel(self, name, reps=20):
         ms, nbytes = C.c_float(), C.c_double()
@@ -475,8 +494,23 @@ def nccl_unique_id():
     return buf.raw
 
 
+class _PinnedOwner:
+    """frees a cudaMallocHost block when the last numpy view of it is gone"""
+
+    def __init__(self, lib, p):
+        self.lib, self.p = lib, p
+
+    def __del__(self):
+        try:
+            self.lib.f2d_host_free(self.p)
+        except Exception:
+            pass
+
+
 def pinned_empty(shape, dtype=np.float64, exact=False):
-    """numpy array backed by page-locked host memory (cudaMallocHost)."""
+    """numpy array backed by page-locked host memory (cudaMallocHost).  The block
+    belongs to the ctypes buffer the array is a view of: it is released
+    (f2d_host_free) when the array and every view derived from it are gone."""
     lib = load(exact)
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p()
@@ -484,9 +518,5 @@ def pinned_empty(shape, dtype=np.float64, exact=False):
     if st != 0:
         raise F2DError(st, lib.f2d_last_error().decode())
     buf = (C.c_char * n).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _pinned_keepalive[arr.ctypes.data] = (p, lib)
-    return arr
-
-
-_pinned_keepalive = {}
+    buf._owner = _PinnedOwner(lib, p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)

@@ -30,24 +30,47 @@ def _stale(target):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(nvcc, flags, src, obj):
+    subprocess.check_call([nvcc, *flags, "-c", "-o", obj, src])
+    return obj
+
+
 def build_one(exact=False, force=False, verbose=False):
+    """one object per translation unit (compiled in parallel, rebuilt only when the
+    source or a header is newer), linked into the shared library"""
     out = lib_path(exact)
     if not force and not _stale(out):
         return out
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-           "-cudart", "static", *ARCH]
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
     if exact:
-        cmd += ["-fmad=false", "-DF2D_EXACT"]
+        flags += ["-fmad=false", "-DF2D_EXACT"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    subprocess.check_call(cmd)
+        flags += ["-Xptxas", "-v"]
+    objdir = os.path.join(HERE, "build", "exact" if exact else "prod")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    jobs = []
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = []
+        for src in SOURCES:
+            sp, ob = os.path.join(CSRC, src), os.path.join(objdir, src[:-3] + ".o")
+            objs.append(ob)
+            if force or not os.path.exists(ob) or os.path.getmtime(ob) < max(os.path.getmtime(sp), hdr_t):
+                jobs.append(pool.submit(_compile, nvcc, flags, sp, ob))
+        for j in jobs:
+            j.result()
+    subprocess.check_call([nvcc, "-shared", "-cudart", "static", *ARCH, "-o", out, *objs, "-ldl"])
     return out
 
 
 def build_all(force=False, verbose=False):
-    return [build_one(False, force, verbose), build_one(True, force, verbose)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        jobs = [pool.submit(build_one, e, force, verbose) for e in (False, True)]
+        return [j.result() for j in jobs]
 
 
 if __name__ == "__main__":

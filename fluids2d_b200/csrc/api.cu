@@ -1,6 +1,7 @@
 // extern "C" surface of libf2d.so (see include/f2d.h).
 #include <algorithm>
 #include <cstring>
+#include <stdexcept>
 
 #include "engine.cuh"
 
@@ -21,6 +22,27 @@ using namespace f2d;
             return F2D_ERR_ARG;        \
         }                              \
     } while (0)
+
+// Every entry point that takes a context makes the context's device current
+// (two Models with different param.device may share a process,
+// tools.run_twin_experiments) and keeps C++ exceptions (std::map::at on a field
+// the model does not have, bad_alloc) on this side of the C boundary.
+#define CTX_ENTER(c)                                        \
+    NEED(c, "null ctx");                                    \
+    F2D_CUDA(cudaSetDevice((c)->cfg.device))
+
+template <class Fn>
+static int guarded(Fn &&fn) {
+    try {
+        return fn();
+    } catch (const std::out_of_range &) {
+        set_error("a field or mesh array this call needs does not exist for this model");
+        return F2D_ERR_ARG;
+    } catch (const std::exception &e) {
+        set_error("internal error: %s", e.what());
+        return F2D_ERR_STATE;
+    }
+}
 
 static const char *MESH_NAMES[] = {"msk", "mskx", "msky", "mskv", "slip", "oc.x", "oc.y",
                                    "ov.x", "ov.y", "ok.x", "ok.y"};
@@ -135,13 +157,13 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     F2D_CUDA(cudaMemsetAsync(c->hb, 0, c->n * sizeof(double), c->stream));
     if (cfg->model == F2D_MODEL_EULER || cfg->model == F2D_MODEL_BOUSSINESQ)
         for (int t = 0; t < 2; t++) F2D_CUDA(cudaMalloc(&c->tmp[t], c->n * sizeof(double)));
-    F2D_CUDA(cudaMalloc(&c->d_scal, 32 * sizeof(double)));
-    F2D_CUDA(cudaMemsetAsync(c->d_scal, 0, 32 * sizeof(double), c->stream));
+    F2D_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+    F2D_CUDA(cudaMemsetAsync(c->d_scal, 0, 64 * sizeof(double), c->stream));
     c->part_capacity = std::max<size_t>(4 * 8192, 4 * (c->n / (40 * 40) + 1024));
     F2D_CUDA(cudaMalloc(&c->d_part, c->part_capacity * sizeof(double)));
     F2D_CUDA(cudaMalloc(&c->d_count, sizeof(unsigned int)));
     F2D_CUDA(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned int), c->stream));
-    F2D_CUDA(cudaMallocHost(&c->h_scal, 32 * sizeof(double)));
+    F2D_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
     F2D_CUDA(cudaMallocHost(&c->h_hist, 512 * sizeof(double)));
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     return F2D_OK;
@@ -179,21 +201,19 @@ int f2d_destroy(f2d_ctx *c) {
 }
 
 int f2d_set_stream(f2d_ctx *c, void *s) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return F2D_OK;
 }
 
 int f2d_sync(f2d_ctx *c) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     return F2D_OK;
 }
 
-int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
-    NEED(c, "null ctx");
-    F2D_CUDA(cudaSetDevice(c->cfg.device));
+static int set_mask_impl(f2d_ctx *c, const int8_t *h_msk) {
     if (c->dist.on) {   // neighbours map my arrays: unmap everywhere before anything is freed
         p2p_teardown(c);
         F2D_TRY(dist_allreduce(c, c->d_scal + 26, 1, false));
@@ -230,8 +250,14 @@ int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
     return F2D_OK;
 }
 
+int f2d_set_mask(f2d_ctx *c, const int8_t *h_msk) {
+    CTX_ENTER(c);
+    return guarded([&] { return set_mask_impl(c, h_msk); });
+}
+
 int f2d_get_mesh_array(f2d_ctx *c, const char *name, int8_t *h_out) {
     NEED(c && name && h_out, "null argument");
+    CTX_ENTER(c);
     auto it = c->mesh.find(name);
     NEED(it != c->mesh.end(), "unknown mesh array '%s'", name);
     F2D_CUDA(cudaMemcpyAsync(h_out, it->second, c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -240,7 +266,7 @@ int f2d_get_mesh_array(f2d_ctx *c, const char *name, int8_t *h_out) {
 }
 
 int f2d_set_topography(f2d_ctx *c, const double *h_hb) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     if (h_hb) F2D_CUDA(cudaMemcpyAsync(c->hb, h_hb, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     else F2D_CUDA(cudaMemsetAsync(c->hb, 0, c->n * sizeof(double), c->stream));
     F2D_CUDA(cudaStreamSynchronize(c->stream));
@@ -249,6 +275,7 @@ int f2d_set_topography(f2d_ctx *c, const double *h_hb) {
 
 static int find_field(f2d_ctx *c, const char *field, double **p) {
     NEED(c && field, "null argument");
+    F2D_CUDA(cudaSetDevice(c->cfg.device));
     auto it = c->fields.find(field);
     NEED(it != c->fields.end(), "unknown field '%s' for this model", field);
     *p = it->second;
@@ -275,23 +302,25 @@ int f2d_download_f32(f2d_ctx *c, const char *field, float *h_dst) {
     double *p;
     F2D_TRY(find_field(c, field, &p));
     NEED(h_dst, "null destination");
-    return download_f32(c, p, field, h_dst);
+    return guarded([&] { return download_f32(c, p, field, h_dst); });
 }
 
 int f2d_set_forcing(f2d_ctx *c, const char *leaf, const double *h_pattern, double amplitude) {
     NEED(c && leaf, "null argument");
-    return set_forcing(c, leaf, h_pattern, amplitude);
+    CTX_ENTER(c);
+    return guarded([&] { return set_forcing(c, leaf, h_pattern, amplitude); });
 }
 
 int f2d_io_sync(f2d_ctx *c) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     if (c->io_stream) F2D_CUDA(cudaStreamSynchronize(c->io_stream));
     return F2D_OK;
 }
 
 int f2d_bulk_sums(f2d_ctx *c, int row0, double *out6) {
     NEED(c && out6, "null argument");
-    return bulk_sums(c, row0, out6);
+    CTX_ENTER(c);
+    return guarded([&] { return bulk_sums(c, row0, out6); });
 }
 
 int f2d_field_ptr(f2d_ctx *c, const char *field, double **d_ptr) {
@@ -300,38 +329,42 @@ int f2d_field_ptr(f2d_ctx *c, const char *field, double **d_ptr) {
 }
 
 int f2d_step(f2d_ctx *c, double dt, int nsteps) {
-    NEED(c, "null ctx");
-    return model_step(c, dt, nsteps);
+    CTX_ENTER(c);
+    return guarded([&] { return model_step(c, dt, nsteps); });
 }
 int f2d_step_lfra(f2d_ctx *c, double dt, int first, double gamma) {
-    NEED(c, "null ctx");
-    return model_step_lfra(c, dt, first, gamma);
+    CTX_ENTER(c);
+    return guarded([&] { return model_step_lfra(c, dt, first, gamma); });
 }
 int f2d_rhs(f2d_ctx *c, int k) {
-    NEED(c, "null ctx");
-    return model_rhs(c, k);
+    CTX_ENTER(c);
+    return guarded([&] { return model_rhs(c, k); });
 }
 int f2d_addto(f2d_ctx *c, int ncoef, const double *coefs) {
     NEED(c && coefs, "null argument");
-    return model_addto(c, ncoef, coefs);
+    CTX_ENTER(c);
+    return guarded([&] { return model_addto(c, ncoef, coefs); });
 }
 int f2d_diag(f2d_ctx *c) {
-    NEED(c, "null ctx");
-    return model_diag(c);
+    CTX_ENTER(c);
+    return guarded([&] { return model_diag(c); });
 }
 int f2d_max_abs_U(f2d_ctx *c, double *h_out) {
     NEED(c && h_out, "null argument");
-    return max_abs_U(c, h_out);
+    CTX_ENTER(c);
+    return guarded([&] { return max_abs_U(c, h_out); });
 }
 
 int f2d_solve(f2d_ctx *c, int which, const double *d_b, double bscale, double *d_x, int *iters,
               double *relres) {
     NEED(c && d_b && d_x, "null argument");
-    return mg_solve(c, which, d_b, bscale, d_x, iters, relres);
+    CTX_ENTER(c);
+    return guarded([&] { return mg_solve(c, which, d_b, bscale, d_x, iters, relres); });
 }
 int f2d_apply_laplacian(f2d_ctx *c, int which, const double *d_x, double *d_y) {
     NEED(c && d_x && d_y, "null argument");
-    return mg_apply(c, which, d_x, d_y);
+    CTX_ENTER(c);
+    return guarded([&] { return mg_apply(c, which, d_x, d_y); });
 }
 int f2d_solver_stats(f2d_ctx *c, int64_t *nsolves, int64_t *niters, double *max_relres) {
     NEED(c, "null ctx");
@@ -343,24 +376,39 @@ int f2d_solver_stats(f2d_ctx *c, int64_t *nsolves, int64_t *niters, double *max_
     return F2D_OK;
 }
 
+int f2d_solver_info(f2d_ctx *c, int which, int *ncomponents, int *nlevels, double *rhs_incompat) {
+    NEED(c, "null ctx");
+    NEED(which >= 0 && which <= 2, "solver id %d", which);
+    const Multigrid &M = c->mg[which];
+    NEED(M.built, "solver %d not built", which);
+    if (ncomponents) *ncomponents = M.ncomp;
+    if (nlevels) *nlevels = (int)M.lev.size() + (c->dist.on ? (int)M.glev.size() - 1 : 0);
+    if (rhs_incompat) *rhs_incompat = M.rhs_incompat;
+    return F2D_OK;
+}
+
 int f2d_compflux(f2d_ctx *c, double *flx, const double *U, const double *q, const int8_t *o,
                  int64_t n, int64_t s, int method) {
     NEED(c && flx && U && q && o, "null argument");
-    return op_compflux(c, flx, U, q, o, (long)n, (long)s, method);
+    CTX_ENTER(c);
+    return guarded([&] { return op_compflux(c, flx, U, q, o, (long)n, (long)s, method); });
 }
 int f2d_vortexforce(f2d_ctx *c, double *du, const double *V, const double *q, const int8_t *o,
                     int64_t n, int64_t s, int64_t s2, int sign, int method) {
     NEED(c && du && V && q && o, "null argument");
-    return op_vortexforce(c, du, V, q, o, (long)n, (long)s, (long)s2, sign, method);
+    CTX_ENTER(c);
+    return guarded([&] { return op_vortexforce(c, du, V, q, o, (long)n, (long)s, (long)s2, sign, method); });
 }
 int f2d_innerproduct(f2d_ctx *c, double *ke, const double *U, const double *q, const int8_t *o,
                      int64_t n, int64_t s, int method) {
     NEED(c && ke && U && q && o, "null argument");
-    return op_innerproduct(c, ke, U, q, o, (long)n, (long)s, method);
+    CTX_ENTER(c);
+    return guarded([&] { return op_innerproduct(c, ke, U, q, o, (long)n, (long)s, method); });
 }
 int f2d_fill(f2d_ctx *c, double *d_a) {
     NEED(c && d_a, "null argument");
-    return op_fill(c, d_a);
+    CTX_ENTER(c);
+    return guarded([&] { return op_fill(c, d_a); });
 }
 
 int f2d_malloc(f2d_ctx *c, size_t bytes, void **d_ptr) {
@@ -370,17 +418,19 @@ int f2d_malloc(f2d_ctx *c, size_t bytes, void **d_ptr) {
     return F2D_OK;
 }
 int f2d_free(f2d_ctx *c, void *d_ptr) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     F2D_CUDA(cudaFree(d_ptr));
     return F2D_OK;
 }
 int f2d_memcpy_h2d(f2d_ctx *c, void *d_dst, const void *h_src, size_t bytes) {
     NEED(c && d_dst && h_src, "null argument");
+    CTX_ENTER(c);
     F2D_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
     return F2D_OK;
 }
 int f2d_memcpy_d2h(f2d_ctx *c, void *h_dst, const void *d_src, size_t bytes) {
     NEED(c && h_dst && d_src, "null argument");
+    CTX_ENTER(c);
     F2D_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     return F2D_OK;
@@ -395,12 +445,13 @@ int f2d_host_free(void *h_ptr) {
     return F2D_OK;
 }
 int f2d_timer_start(f2d_ctx *c) {
-    NEED(c, "null ctx");
+    CTX_ENTER(c);
     F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
     return F2D_OK;
 }
 int f2d_timer_stop(f2d_ctx *c, float *ms) {
     NEED(c && ms, "null argument");
+    CTX_ENTER(c);
     F2D_CUDA(cudaEventRecord(c->ev1, c->stream));
     F2D_CUDA(cudaEventSynchronize(c->ev1));
     F2D_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -408,8 +459,11 @@ int f2d_timer_stop(f2d_ctx *c, float *ms) {
 }
 int f2d_bench_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *alg_bytes) {
     NEED(c && name && ms && alg_bytes && reps > 0, "bad argument");
-    if (!strncmp(name, "mg.", 3) || !strncmp(name, "cg.", 3)) return bench_mg_kernel(c, name, reps, ms, alg_bytes);
-    return bench_step_kernel(c, name, reps, ms, alg_bytes);
+    CTX_ENTER(c);
+    return guarded([&] {
+        if (!strncmp(name, "mg.", 3) || !strncmp(name, "cg.", 3)) return bench_mg_kernel(c, name, reps, ms, alg_bytes);
+        return bench_step_kernel(c, name, reps, ms, alg_bytes);
+    });
 }
 int f2d_dist_unique_id(char *id128) {
     NEED(id128, "null argument");
@@ -418,7 +472,8 @@ int f2d_dist_unique_id(char *id128) {
 int f2d_dist_init(f2d_ctx *c, int rank, int world, const char *id128) {
     NEED(c && id128, "null argument");
     NEED(!c->mesh_ready, "f2d_dist_init must precede f2d_set_mask");
-    return dist_init(c, rank, world, id128);
+    CTX_ENTER(c);
+    return guarded([&] { return dist_init(c, rank, world, id128); });
 }
 int f2d_dist_exchange(f2d_ctx *c, const char *field) {
     double *p;

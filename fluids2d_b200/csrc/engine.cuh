@@ -125,6 +125,15 @@ struct Multigrid {
     float *zf = nullptr, *zf2 = nullptr;   // preconditioned residual z = M r: fp32 (mg_tiles.cuh)
     int tail = 1;                     // first level handled by the single-CTA tail kernel
     int64_t nunknown = 0;
+    // Neumann null space: one constant per CONNECTED fluid component (elliptic.py:186-190 gives
+    // every component its own singular block).  One component: the mean is removed lazily
+    // inside the kernels.  Several: `comp` labels the unknowns of the MAXCOMP largest
+    // components (0xFF elsewhere) and r, z are projected explicitly per component.
+    static constexpr int MAXCOMP = 8;
+    int ncomp = 1;                    // connected components of the unknowns
+    uint8_t *comp = nullptr;          // (n2,n1), only when ncomp > 1
+    double inv_nc[MAXCOMP] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double rhs_incompat = 0;          // max_c |sum_c b| / sqrt(N_c b.b) over the solves so far
 };
 
 }  // namespace f2d

@@ -1234,7 +1234,8 @@ int bulk_sums(f2d_ctx *c, int row0, double *out) {
         return F2D_ERR_UNSUPPORTED;
     }
     int gs = c->cfg.reserved[1], gn = c->cfg.reserved[2];
-    int j0 = gs > 0 ? c->nh + gs : 0, j1 = gn > 0 ? c->n2 - c->nh - gn : c->n2;
+    // at an interface the local array is [G ghost rows | owned rows | G ghost rows] with no wall halo on that side
+    int j0 = gs > 0 ? gs : 0, j1 = gn > 0 ? c->n2 - gn : c->n2;
     int nb = c->nsm * 4;
     k_bulk<<<nb, 256, 0, c->stream>>>(c->n1, j0, j1, c->nh, row0, c->dx, c->dy, c->f("ke"), c->f("omega"),
                                       c->f("U.x"), c->f("U.y"), c->m("msk"), c->d_part, c->d_count, c->d_scal + 16);
@@ -1285,30 +1286,47 @@ int download_f32(f2d_ctx *c, const double *src, const std::string &key, float *h
 // ---------------------------------------------------------------------------
 int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *bytes) {
     if (!c->mesh_ready) { set_error("bench before f2d_set_mask"); return F2D_ERR_STATE; }
-    if (c->cfg.model != F2D_MODEL_EULER || c->nstages != 3) {
-        set_error("kernel benches are defined for the euler model with a 3-stage integrator");
+    const int model = c->cfg.model;
+    const bool proj = model == F2D_MODEL_EULER || model == F2D_MODEL_BOUSSINESQ;       // projecting models: fused stage
+    const bool sw = model == F2D_MODEL_RSW || model == F2D_MODEL_QGRSW;
+    if (!(proj || sw) || c->nstages != 3) {
+        set_error("kernel benches are defined for euler, boussinesq, rsw and qgrsw with a 3-stage integrator");
         return F2D_ERR_UNSUPPORTED;
     }
     std::string k(name);
     Grid g = grid_of(c);
     double npts = (double)c->n;
     if (k == "project_diag") {
+        if (!proj) { set_error("'%s' belongs to the projecting models", name); return F2D_ERR_ARG; }
         F2D_CUDA(cudaMemcpyAsync(c->tmp[0], c->f("u.x"), c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
         F2D_CUDA(cudaMemcpyAsync(c->tmp[1], c->f("u.y"), c->n * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
+    const char *scalar = model == F2D_MODEL_BOUSSINESQ ? "b" : "h";       // the flux-form scalar of the model
     for (int pass = 0; pass < 2; pass++) {   // pass 0 = warm-up
         int n = pass == 0 ? 2 : reps;
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < n; r++) {
-            if (k == "advection") {
+            if (k == "advection" && proj) {
                 // stage 2 of rk3, fused with the RK update:
-                // R u.x u.y omega ke ds0.x ds0.y, W ds1.x ds1.y ub.x ub.y, masks ov.x ov.y mskx msky
+                // R u.x u.y omega ke ds0.x ds0.y [b], W ds1.x ds1.y ub.x ub.y, masks ov.x ov.y mskx msky
                 RkFuse rk;
                 rk.c[0] = rk.c[1] = rk.c[2] = 0.0;
                 rk.dx[0] = c->f("ds0.u.x"); rk.dy[0] = c->f("ds0.u.y"); rk.dx[1] = rk.dy[1] = nullptr;
                 rk.ubx = c->tmp[0]; rk.uby = c->tmp[1]; rk.write_ds = 1;
-                F2D_TRY((launch_stage_tiled<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
-                *bytes = npts * (10 * 8 + 4);
+                if (model == F2D_MODEL_EULER) F2D_TRY((launch_stage_tiled<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
+                else F2D_TRY((launch_stage_tiled<M_BOUSS, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
+                *bytes = npts * ((model == F2D_MODEL_EULER ? 10 : 11) * 8 + 4);
+            } else if (k == "advection") {
+                // rsw / qgrsw momentum tendency (vortex force + Coriolis [+ grad(ke + p)]), no fused update:
+                // R u.x u.y omega [ke p], W ds.x ds.y, masks ov.x ov.y mskx msky
+                if (model == F2D_MODEL_RSW) F2D_TRY((launch_rhs_mom<M_RSW>(c, c->f("ds1.u.x"), c->f("ds1.u.y"))));
+                else F2D_TRY((launch_rhs_mom<M_QGRSW>(c, c->f("ds1.u.x"), c->f("ds1.u.y"))));
+                *bytes = npts * ((model == F2D_MODEL_RSW ? 7 : 5) * 8 + 4);
+            } else if (k == "flux_div" && (sw || model == F2D_MODEL_BOUSSINESQ)) {
+                // divflux of the advected scalar, two kernels: R u.x u.y q, W flx.x flx.y (oc.x oc.y);
+                // R flx.x flx.y, W dq (msk)
+                F2D_TRY(launch_divflux(c, c->f(scalar), c->f(dsname(1, scalar))));
+                *bytes = npts * (8 * 8 + 3);
             } else if (k == "rk_update") {
                 // R u ds0 ds1 ds2, W u (one component; coefficients 0 keep u intact)
                 long n1 = (long)c->n;
@@ -1316,7 +1334,7 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                     n1, c->f("u.x"), c->f("ds0.u.x"), c->f("ds1.u.x"), c->f("ds2.u.x"), 0.0, 0.0, 0.0);
                 LAUNCH_CHECK(c);
                 *bytes = npts * (5 * 8);
-            } else if (k == "divergence") {
+            } else if (k == "divergence" && proj) {
                 // R u.x u.y, W div, mask msk
                 k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("u.x"), c->f("u.y"), c->m("msk"), c->f("div"));
                 LAUNCH_CHECK(c);
@@ -1325,7 +1343,24 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 // R p u.x u.y, W u.x u.y U.x U.y omega ke, masks msk mskx msky slip ok.x ok.y
                 F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
                 *bytes = npts * (9 * 8 + 6);
-            } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
+            } else if (k == "diag" && sw) {
+                // rsw: R u.x u.y h hb, W U.x U.y omega ke p (msk slip ok.x ok.y); qgrsw: R u.x u.y, W U.x U.y omega (slip)
+                if (model == F2D_MODEL_RSW) F2D_TRY((launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct)));
+                else F2D_TRY((launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1)));
+                *bytes = npts * (model == F2D_MODEL_RSW ? 9 * 8 + 4 : 5 * 8 + 1);
+            } else if (k == "qg_pv" && model == F2D_MODEL_QGRSW) {
+                // R du.x du.y dh, W pv (slip mskv)
+                k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("ds1.u.x"), c->f("ds1.u.y"), c->f("ds1.h"), c->m("slip"),
+                                                              c->m("mskv"), -c->cfg.f0 / c->cfg.H, c->f("pv"));
+                LAUNCH_CHECK(c);
+                *bytes = npts * (4 * 8 + 2);
+            } else if (k == "qg_back" && model == F2D_MODEL_QGRSW) {
+                // R psi, W du.x du.y dh (msk mskx msky mskv)
+                k_qg_back<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("msk"), c->m("mskx"), c->m("msky"), c->m("mskv"),
+                                                                c->cfg.f0 * c->area / c->cfg.g, c->f("ds1.u.x"), c->f("ds1.u.y"), c->f("ds1.h"));
+                LAUNCH_CHECK(c);
+                *bytes = npts * (4 * 8 + 4);
+            } else { set_error("unknown kernel '%s' for this model", name); return F2D_ERR_ARG; }
         }
     }
     F2D_CUDA(cudaEventRecord(c->ev1, c->stream));

@@ -47,8 +47,13 @@ class Bulk:
         self.xvyu = (xv, yu)
         self.kt = 0
         self.ncfile = ncfile
-        self.k0 = get_number_of_records(self.ncfile)
-        if self.k0 == 0:
+        # slab mode: the device sums are all-reduced, every rank holds the same
+        # averages -- only rank 0 owns bulk.nc
+        slab = getattr(model.mesh, "slab", None)
+        self.nranks = slab.nranks if slab is not None else 1
+        self.writer = slab is None or slab.rank == 0
+        self.k0 = get_number_of_records(self.ncfile) if self.writer else 0
+        if self.writer and self.k0 == 0:
             self.create_newfile()
 
     def create_newfile(self):
@@ -60,7 +65,13 @@ class Bulk:
         model = self.model
         mesh = model.mesh
         dx, dy, area = mesh.dx, mesh.dy, mesh.area
-        if getattr(model, "_resident", False):
+        resident = getattr(model, "_resident", False)
+        if self.nranks > 1 and not resident:
+            # a slab's host arrays carry ghost rows and a local mask sum: the global
+            # averages come from the owned rows of every rank (f2d_bulk_sums all-reduces)
+            model.integrator.upload(model.state, ["ke", "omega", "U.x", "U.y"])
+            resident = True
+        if resident:
             ske, som2, som, suyx, suxy, smsk = mesh.engine.bulk_sums()
             return (ske / smsk, 0.5 * (som2 / smsk) / area ** 2, (som / smsk) / area,
                     (suyx / smsk) * dx - (suxy / smsk) * dy)
@@ -86,9 +97,10 @@ class Bulk:
     def write(self):
         n = self.kt
         idx = slice(self.k0, self.k0 + n)
-        with _nc.Dataset(self.ncfile, "r+") as nc:
-            for name, x in zip(self.data._fields, self.data):
-                nc.variables[name][idx] = x[:n]
+        if self.writer:
+            with _nc.Dataset(self.ncfile, "r+") as nc:
+                for name, x in zip(self.data._fields, self.data):
+                    nc.variables[name][idx] = x[:n]
         self.k0 += n
         self.kt = 0
 

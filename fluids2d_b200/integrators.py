@@ -120,6 +120,23 @@ class RKIntegrator:
         vomega, work), which need not cross PCIe on the way in"""
         has_u = "u" in state._fields or "uh" in state._fields
         skip = {"div", "flx.x", "flx.y", "vomega", "work"} | ({"U.x", "U.y"} if has_u else set())
+        # solutions of the step's own elliptic solves: the reference's direct solve
+        # overwrites them whatever they hold (elliptic.py:80-87); here they only seed
+        # the iteration, and the device copy of the previous step does that as well
+        if self.param.model in ("euler", "boussinesq"):
+            skip |= {"p"}
+        elif self.param.model == "qgrsw":
+            skip |= {"pv", "psi"}
+        elif self.param.model in ("eulerpsi", "qg"):
+            skip |= {"psi"}
+        return [n for n in self._names(state) if n not in skip]
+
+    def _step_outputs(self, state):
+        """fields a step leaves different on the host: all of them by default, as
+        the reference's in-place step does.  ``integrator.skip_outputs`` (a set of
+        leaf names, empty by default) lets a script that never reads e.g. ``div``
+        or ``U`` between steps keep them off the PCIe bus."""
+        skip = getattr(self, "skip_outputs", None) or ()
         return [n for n in self._names(state) if n not in skip]
 
     def _update_forcings(self, t):
@@ -131,7 +148,7 @@ class RKIntegrator:
             self.upload(state, self._step_inputs(state))
             self._update_forcings(time.t)
             self.engine.step(time.dt, 1)
-            self.download(state)
+            self.download(state, self._step_outputs(state))
         else:
             self._step_with_host_rhs(state, time.dt)
         time.pushforward()

@@ -50,7 +50,7 @@ class Mesh:
     @hb.setter
     def hb(self, value):
         self._hb = value
-        self.engine.set_topography(None if np.isscalar(value) else value)
+        self.engine.set_topography(value)
 
     def _allocate(self):
         return np.zeros(self.shape, dtype="i1")

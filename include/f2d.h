@@ -163,6 +163,12 @@ int f2d_solve(f2d_ctx *ctx, int which, const double *d_b, double bscale, double 
 int f2d_apply_laplacian(f2d_ctx *ctx, int which, const double *d_x, double *d_y);
 /* statistics of the solves issued by f2d_step / f2d_diag since the last call */
 int f2d_solver_stats(f2d_ctx *ctx, int64_t *nsolves, int64_t *niters, double *max_relres);
+/* structure of solver `which`: connected components of its unknowns (the
+ * all-Neumann operator of elliptic.py:186-190 has one null-space constant per
+ * component; each gets its own projection), multigrid levels, and how far the
+ * right-hand sides seen so far were from the operator's range:
+ * max over solves and components of |sum_c b| / sqrt(N_c b.b) (0 = compatible). */
+int f2d_solver_info(f2d_ctx *ctx, int which, int *ncomponents, int *nlevels, double *rhs_incompat);
 
 /* ---- the three kernels of weno.py:412-436, one launch each, flat-index
  *      semantics of the reference (s, s2 are flat strides), device arrays of

@@ -282,17 +282,39 @@ def laplacian(mesh, location, maindiag=0.0):
 
 
 class Poisson2D:
-    """elliptic.py:71-87"""
+    """elliptic.py:71-87.  The reference assembles and factorises in __init__; the
+    oracle does both on first use (same matrix, same SuperLU call), so that a test
+    only pays for the solvers its model actually calls."""
 
     def __init__(self, mesh, location, maindiag=0.0):
-        import scipy.sparse.linalg as spl
-        self.mesh, self.location = mesh, location
-        self.A, self.G = laplacian(mesh, location, maindiag)
-        self.A_LU = spl.splu(self.A)
-        self._k = self.G > -1
+        self.mesh, self.location, self.maindiag = mesh, location, maindiag
+        self._A = self._G = self._LU = None
+
+    def _assemble(self):
+        if self._A is None:
+            self._A, self._G = laplacian(self.mesh, self.location, self.maindiag)
+            self._k = self._G > -1
+
+    @property
+    def A(self):
+        self._assemble()
+        return self._A
+
+    @property
+    def G(self):
+        self._assemble()
+        return self._G
+
+    @property
+    def A_LU(self):
+        if self._LU is None:
+            import scipy.sparse.linalg as spl
+            self._LU = spl.splu(self.A)
+        return self._LU
 
     def solve(self, b, x):
-        x[self._k] = self.A_LU.solve(b[self._k])
+        lu = self.A_LU
+        x[self._k] = lu.solve(b[self._k])
         self.mesh.fill(x)
 
 

@@ -11,16 +11,25 @@ import sys
 import types
 
 REF_SRC = "/root/reference/src"
+# where oracle/install_ref.py puts the UNMODIFIED reference package (git-ignored,
+# travels to the GPU box with the snapshot): bench.py --impl reference runs it
+VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 def available():
     return os.path.isdir(os.path.join(REF_SRC, "fluids2d"))
 
 
-def load():
-    """Return the reference's ``fluids2d`` package (imports numba kernels, ~8 s)."""
-    if not available():
-        raise RuntimeError("reference tree not present")
+def vendored_available():
+    return os.path.isdir(os.path.join(VENDORED, "fluids2d"))
+
+
+def load(src=None):
+    """Return the reference's ``fluids2d`` package (imports numba kernels, ~8 s).
+    `src`: directory that holds the package (default: the live tree)."""
+    src = src or REF_SRC
+    if not os.path.isdir(os.path.join(src, "fluids2d")):
+        raise RuntimeError("reference package not present under " + src)
 
     def stub(name, **attrs):
         if name in sys.modules:
@@ -40,7 +49,7 @@ def load():
     stub("mpl_toolkits")
     stub("mpl_toolkits.axes_grid1", make_axes_locatable=lambda ax: None)
     stub("PIL", Image=None)
-    if REF_SRC not in sys.path:
-        sys.path.insert(0, REF_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import fluids2d  # noqa: E402
     return fluids2d

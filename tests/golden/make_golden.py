@@ -125,6 +125,49 @@ def case_disc_island():
     run_case("disc_island", kw, mask_fn=mask, ic=lambda m: dipole_ic(m, 0.5, 0.6, 0.06, 0.06))
 
 
+def lake_mask(model):
+    """closed box with a wall ring that encloses a lake: two connected fluid
+    components, each with its own Neumann null-space constant (elliptic.py:186-190)"""
+    x, y = model.mesh.xy()
+    msk = model.mesh.msk
+    r = np.sqrt((x - 0.62) ** 2 + (y - 0.55) ** 2)
+    msk[(r > 0.17) & (r < 0.22)] = 0
+
+
+def case_euler_lake():
+    kw = dict(model="euler", nx=72, ny=64, noslip=False)
+
+    def ic(model):
+        x, y = model.mesh.xy("v")
+        om = model.state.omega
+        # a dipole in the basin and a single vortex inside the lake
+        om[:, :] = (gaussian(x, y, 0.25, 0.3, 0.05) - gaussian(x, y, 0.25, 0.42, 0.05)
+                    + 0.8 * gaussian(x, y, 0.6, 0.57, 0.04))
+        om *= model.mesh.mskv * model.mesh.area
+        f2d.tools.set_uv_from_omega(model, om, model.state.u)
+        model.integrator.diag(model.state)
+    run_case("euler_lake", kw, mask_fn=lake_mask, ic=ic)
+
+
+def case_euler_two_basins():
+    # a wall three cells thick splits the box into two disconnected basins
+    kw = dict(model="euler", nx=80, ny=48, Lx=1.6, noslip=True)
+
+    def mask(model):
+        x, y = model.mesh.xy()
+        model.mesh.msk[np.abs(x - 0.7) < 0.03] = 0
+
+    def ic(model):
+        x, y = model.mesh.xy("v")
+        om = model.state.omega
+        om[:, :] = (gaussian(x, y, 0.35, 0.55, 0.06) - gaussian(x, y, 0.35, 0.4, 0.06)
+                    - gaussian(x, y, 1.2, 0.5, 0.07))
+        om *= model.mesh.mskv * model.mesh.area
+        f2d.tools.set_uv_from_omega(model, om, model.state.u)
+        model.integrator.diag(model.state)
+    run_case("euler_two_basins", kw, mask_fn=mask, ic=ic)
+
+
 def case_xper_noslip():
     # non-square cells (dx != dy), odd-ish sizes, per-wall no-slip
     kw = dict(model="euler", nx=72, ny=40, Lx=1.5, Ly=1.0, xperiodic=True, noslip=["bottom"])
@@ -518,7 +561,7 @@ def mesh_vectors():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or None
-    todo = [case_euler40, case_vortex, case_vortex_triangle, case_disc_island, case_xper_noslip,
+    todo = [case_euler40, case_vortex, case_vortex_triangle, case_disc_island, case_euler_lake, case_euler_two_basins, case_xper_noslip,
             case_euler_enrk3_upwind, case_euler_centered_ef, case_euler_cweno,
             case_rsw, case_rsw_islands, case_qgrsw_topo, case_qgrsw_islands,
             case_warm_bubble, case_lock_exchange, case_advection, case_advection_disc_upwind, case_eulerpsi,

@@ -6,7 +6,9 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-EULER_CASES = ["euler40", "vortex", "vortex_triangle", "disc_island", "xper_noslip",
+EULER_CASES = ["euler40", "vortex", "vortex_triangle", "disc_island",
+               # two connected fluid components: one Neumann null-space constant each
+               "euler_lake", "euler_two_basins", "xper_noslip",
                "euler_enrk3_upwind", "euler_centered_ef", "euler_cweno"]
 ALL_CASES = EULER_CASES + ["rsw", "rsw_islands", "qgrsw_topo", "qgrsw_islands",
                            "warm_bubble", "lock_exchange",
