@@ -177,6 +177,7 @@ int f2d_destroy(f2d_ctx *c) {
     dist_free(c);
     for (auto &G : c->guess) for (double *g : G.g) cudaFree(g);
     for (auto &kv : c->mesh) cudaFree(kv.second);
+    for (auto &kv : c->field_home) c->fields[kv.first] = kv.second;     // history slots are freed above
     for (auto &kv : c->fields) cudaFree(kv.second);
     for (auto &kv : c->forcing) cudaFree(kv.second.pattern);
     if (c->io_stream) cudaStreamSynchronize(c->io_stream);
@@ -221,6 +222,10 @@ static int set_mask_impl(f2d_ctx *c, const int8_t *h_msk) {
     }
     F2D_TRY(build_mesh(c, h_msk));
     for (auto &G : c->guess) G.valid = 0;     // a new mask invalidates the solve history
+    for (auto &kv : c->field_home) {          // fields living in a history slot go home (contents do not matter:
+        c->fields[kv.first] = kv.second;       // a new mask restarts from whatever first guess the caller uploads)
+    }
+    c->field_home.clear();
     // meshes.py:39-47
     F2D_TRY(mg_build(c, F2D_SOLVER_CENTERS));
     F2D_TRY(mg_build(c, F2D_SOLVER_VERTICES));
@@ -238,8 +243,8 @@ static int set_mask_impl(f2d_ctx *c, const int8_t *h_msk) {
         for (int w = 0; w < 3; w++) {
             Multigrid &M = c->mg[w];
             if (!M.built) continue;
-            for (double *p : {M.r, M.z, M.p, M.p2, M.q}) add(p, c->n2, 0, fb);
-            for (float *p : {M.zf, M.zf2}) add(p, c->n2, 0, (long long)c->n1 * sizeof(float));
+            for (double *p : {M.r, M.z, M.q}) add(p, c->n2, 0, fb);
+            for (float *p : {M.zf, M.zf2, M.p, M.p2}) add(p, c->n2, 0, (long long)c->n1 * sizeof(float));
             for (size_t l = 1; l < M.lev.size(); l++) {
                 Level &L = M.lev[l];
                 for (CT *p : {L.x, L.x2, L.b}) add(p, L.ny + 2, 1, (long long)L.pitch * sizeof(CT));
@@ -278,6 +283,7 @@ static int find_field(f2d_ctx *c, const char *field, double **p) {
     F2D_CUDA(cudaSetDevice(c->cfg.device));
     auto it = c->fields.find(field);
     NEED(it != c->fields.end(), "unknown field '%s' for this model", field);
+    if (c->U_stale && (!strcmp(field, "U.x") || !strcmp(field, "U.y"))) F2D_TRY(ensure_U(c));   // formed on demand
     *p = it->second;
     return F2D_OK;
 }
@@ -379,11 +385,11 @@ int f2d_solver_stats(f2d_ctx *c, int64_t *nsolves, int64_t *niters, double *max_
 int f2d_solver_info(f2d_ctx *c, int which, int *ncomponents, int *nlevels, double *rhs_incompat) {
     NEED(c, "null ctx");
     NEED(which >= 0 && which <= 2, "solver id %d", which);
-    const Multigrid &M = c->mg[which];
+    Multigrid &M = c->mg[which];
     NEED(M.built, "solver %d not built", which);
     if (ncomponents) *ncomponents = M.ncomp;
     if (nlevels) *nlevels = (int)M.lev.size() + (c->dist.on ? (int)M.glev.size() - 1 : 0);
-    if (rhs_incompat) *rhs_incompat = M.rhs_incompat;
+    if (rhs_incompat) { *rhs_incompat = M.rhs_incompat; M.rhs_incompat = 0.0; }    // since the last call
     return F2D_OK;
 }
 

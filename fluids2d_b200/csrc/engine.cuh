@@ -115,13 +115,14 @@ struct Multigrid {
     int jo0 = 0, jo1 = 0;             // owned logical rows of the fine level [jo0, jo1)
     int tail_y0 = 0;                  // slab mode: first owned row of level `tail` in the global tail grid
     double n_global = 0;              // unknowns over all ranks
-    // CUDA graphs of one PCG iteration (first / odd / even), keyed by the solution array
-    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
-    const double *gx[3] = {nullptr, nullptr, nullptr};
-    int64_t glaunches[3] = {0, 0, 0}, gexchanges[3] = {0, 0, 0};
+    // CUDA graphs of one PCG iteration, keyed by (solution array, first / odd / even iteration):
+    // inside f2d_step the solution array rotates through the first-guess history slots
+    struct IterGraph { const double *x; int cls; cudaGraphExec_t exec; int64_t launches, exchanges; };
+    std::vector<IterGraph> graphs;
     bool warm = false;
     int expect = 0;        // iterations the previous solve needed: that many run without a host check
-    double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr, *p2 = nullptr;   // CG vectors (n2,n1)
+    double *r = nullptr, *z = nullptr, *q = nullptr;   // CG residual; work vectors of the un-fused cross-check path (n2,n1)
+    float *p = nullptr, *p2 = nullptr;                 // CG search direction, ping-pong, fp32 (mg.cu: k_cg_dir_apply)
     float *zf = nullptr, *zf2 = nullptr;   // preconditioned residual z = M r: fp32 (mg_tiles.cuh)
     int tail = 1;                     // first level handled by the single-CTA tail kernel
     int64_t nunknown = 0;
@@ -139,11 +140,21 @@ struct Multigrid {
 }  // namespace f2d
 
 namespace f2d {
-struct GuessHistory {            // last solutions of one RK stage's elliptic solve
-    double *g[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double t[6] = {0, 0, 0, 0, 0, 0};     // model time and step length each was computed at
-    double dt[6] = {1, 1, 1, 1, 1, 1};
+// Last solutions of one RK stage's elliptic solve.  The solver works IN the slot that
+// becomes the newest entry (the oldest one, which the extrapolation no longer reads), so a
+// solution is never copied into the history: depth = extrapolation order + 1.
+struct GuessHistory {
+    static constexpr int MAXD = 7;
+    double *g[MAXD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double t[MAXD] = {0, 0, 0, 0, 0, 0, 0};     // model time and step length each was computed at
+    double dt[MAXD] = {1, 1, 1, 1, 1, 1, 1};
     int valid = 0;
+};
+// first guess x0 = sum_k w[k] g[k] (k < n), formed inside the initial-residual kernel
+struct GuessSpec {
+    const double *g[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double w[6] = {0, 0, 0, 0, 0, 0};
+    int n = 0;
 };
 }  // namespace f2d
 
@@ -162,6 +173,10 @@ struct f2d_ctx {
     bool mesh_ready = false;
     // state + scratch (float64, (n2,n1))
     std::map<std::string, double *> fields;
+    // a field whose storage currently is a first-guess history slot (step.cu: guess_begin):
+    // its own allocation, to be handed back / freed
+    std::map<std::string, double *> field_home;
+    bool U_stale = false;                    // U = sharp(u) is formed on demand (step.cu: ensure_U)
     std::vector<std::string> prognostic;     // leaf names, e.g. "u.x","u.y"
     int nstages = 3;
     double *hb = nullptr;                    // topography (zeros by default)
@@ -215,7 +230,8 @@ int download_f32(f2d_ctx *c, const double *src, const std::string &key, float *h
 int mg_build(f2d_ctx *c, int which);
 void mg_free(f2d_ctx *c, int which);
 int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters,
-             double *relres);
+             double *relres, const GuessSpec *guess = nullptr);
+int ensure_U(f2d_ctx *c);
 int mg_apply(f2d_ctx *c, int which, const double *x, double *y);
 // dist.cu
 int dist_exchange(f2d_ctx *c, int narr, void *const *base, size_t row_bytes, long nrows, long row0);

@@ -373,58 +373,251 @@ __device__ __forceinline__ double cg_diag(const FineView &F, double cw, double c
                        : __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(cw, ce), cs), cn), F.shift);
 }
 
+// The search direction is STORED in fp32 (the preconditioned residual z already is):
+//   pnew = fl32((z - mean z) + beta pold)
+// and q = L pnew is never stored: k_cg_dir_apply only needs its dot product with pnew,
+// the update kernel re-applies the 5-point operator to the fp32 window it reads anyway.
+// L pnew itself is evaluated in fp64 in both (for smooth p it is a difference of nearly
+// equal numbers: in fp32 the cancellation left p.q -- and with it alpha -- without a
+// single correct digit on a 4096^2 grid, and CG diverged).  Per fine
+// point the two CG kernels move 13 + 37 bytes instead of 29 + 49.  x and r stay fp64 and
+// are updated with the SAME rounded direction (x += alpha p, r -= alpha L p with L p in
+// fp64), so r remains the residual of x to fp64 rounding whatever alpha is; the rounding
+// of p and alpha only perturbs the conjugacy of successive directions at the 1e-7 level,
+// far below what the 4-5 iterations of a solve can see.
+//
 //   tile_open[tile] != 0 (k_cg_tile_flags): the whole window lies inside the array, needs
-//   no periodic wrap and holds unknowns only -> no mask bytes, no bounds tests, and the
-//   loads do not wait for a mask byte first.  Same arithmetic, same bits.
+//   no periodic wrap and holds unknowns only -> no mask bytes, no bounds tests, NO shared
+//   memory and no barrier: a thread owns 4 consecutive rows of one column, issues all its
+//   loads first, and gets its W / E neighbours from the adjacent lanes (the two edge lanes
+//   of a warp load theirs).  Both paths evaluate the same expressions with the same
+//   thread-to-row map: same bits, whichever tiles are open.
+struct CgF32 { float mz, beta; };
 template <typename TZ>
-__global__ void __launch_bounds__(256, 6)
-k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ pold,
-               double *__restrict__ pnew, double *__restrict__ q, double *__restrict__ scal, int it,
+__device__ __forceinline__ float cg_pnew32(TZ z, float pold, const CgF32 &K, double mz, double beta) {
+    if constexpr (sizeof(TZ) == 4) return __fmaf_rn(K.beta, pold, __fsub_rn((float)z, K.mz));
+    else return (float)cg_pnew((double)z, mz, beta, (double)pold);      // un-fused cross-check path: z is fp64
+}
+
+template <typename TZ>
+__global__ void __launch_bounds__(256, 4)
+k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ pold,
+               float *__restrict__ pnew, double *__restrict__ scal, int it,
                int singular, double inv_n, double *part, unsigned int *count,
                const uint8_t *__restrict__ tile_open) {
-    __shared__ double sp[CGY + 2][CGX + 2];
+    __shared__ float sp[CGY + 2][CGX + 2];
     double rznew = scal[S_RZNEW];
     double mz = singular ? scal[S_SUMZ] * inv_n : 0.0;
     double beta = 0.0;
     if (it > 0) { double rzold = scal[S_RZ0 + ((it - 1) & 1)]; beta = rzold != 0.0 ? rznew / rzold : 0.0; }
+    const CgF32 K{(float)mz, (float)beta};
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY, ntiles = ntx * nty;
+    const int stride = gridDim.x * gridDim.y;
+    const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
+    constexpr int R = CGY / 4;
+    double v[1] = {0.0};
+    int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    uint8_t flag = (tile_open != nullptr && tile < ntiles) ? tile_open[tile] : 0;
+    for (; tile < ntiles; tile += stride) {
+        const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
+        const bool open = flag != 0;                                    // block-uniform
+        if (tile_open != nullptr && tile + stride < ntiles) flag = tile_open[tile + stride];   // in flight during this tile
+        if (open) {
+            const int lane = threadIdx.x & 31;
+            const long idx0 = (long)(F.oj + j0 + R * threadIdx.y - 1) * F.n1 + F.oi + i0 + threadIdx.x;   // row above my first
+            TZ zv[R + 2], zw[R];
+            float pv[R + 2], pw[R];
+#pragma unroll
+            for (int u = 0; u < R + 2; u++) { zv[u] = z[idx0 + (long)u * F.n1]; pv[u] = pold[idx0 + (long)u * F.n1]; }
+            const int side = lane == 0 ? -1 : 1;
+            if (lane == 0 || lane == 31) {
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    zw[u] = z[idx0 + (long)(u + 1) * F.n1 + side];
+                    pw[u] = pold[idx0 + (long)(u + 1) * F.n1 + side];
+                }
+            }
+            float pn[R + 2];
+#pragma unroll
+            for (int u = 0; u < R + 2; u++) pn[u] = cg_pnew32<TZ>(zv[u], pv[u], K, mz, beta);
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int j = j0 + R * threadIdx.y + u;
+                const float pf = pn[u + 1];
+                float w = __shfl_up_sync(0xffffffffu, pf, 1), e = __shfl_down_sync(0xffffffffu, pf, 1);
+                if (lane == 0) w = cg_pnew32<TZ>(zw[u], pw[u], K, mz, beta);
+                if (lane == 31) e = cg_pnew32<TZ>(zw[u], pw[u], K, mz, beta);
+                pnew[idx0 + (long)(u + 1) * F.n1] = pf;
+                const double pc = (double)pf;
+                const double qv = cg_q(F, diag_open, pc, (double)w, (double)e, (double)pn[u], (double)pn[u + 2]);
+                if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
+            }
+            continue;
+        }
+        __syncthreads();        // the previous masked tile of this CTA is done with sp
+        for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
+            int a = t / (CGX + 2), b = t - a * (CGX + 2);
+            int j = j0 - 1 + a, i = i0 - 1 + b;
+            if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            float pv = 0.0f;
+            long idx;
+            if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF))
+                pv = cg_pnew32<TZ>(z[idx], pold[idx], K, mz, beta);
+            sp[a][b] = pv;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int a = 1 + R * threadIdx.y + r, b = 1 + threadIdx.x, j = j0 + R * threadIdx.y + r;   // the open path's thread-to-row map
+            long idx;
+            if (i >= F.nx || j >= F.ny || !fine_index(F, j, i, idx)) continue;
+            uint8_t c = F.nb[idx];
+            if (!(c & NB_SELF)) continue;
+            double cw = (c & NB_W) ? F.cx : 0.0, ce = (c & NB_E) ? F.cx : 0.0;
+            double cs = (c & NB_S) ? F.cy : 0.0, cn = (c & NB_N) ? F.cy : 0.0;
+            const double diag = cg_diag(F, cw, ce, cs, cn);
+            const float pf = sp[a][b];
+            const double pc = (double)pf;
+            pnew[idx] = pf;
+            // closed faces lead to points that are not unknowns: their sp entry is 0
+            const double qv = cg_q(F, diag, pc, (double)sp[a][b - 1], (double)sp[a][b + 1], (double)sp[a - 1][b], (double)sp[a + 1][b]);
+            if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
+        }
+    }
+    grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) scal[S_RZ0 + (it & 1)] = rznew;
+}
+
+// x += alpha p ; r -= alpha L p ; (rr, sum r)          alpha = rz / pq.   L p in fp64 from
+// the fp32 direction; same tiles and thread-to-row map as k_cg_dir_apply.
+__global__ void __launch_bounds__(256, 4)      // 64 registers: at 40 the loaded window was spilled as it arrived
+k_cg_update_p(FineView F, double *__restrict__ x, double *__restrict__ r, const float *__restrict__ p,
+              const double *__restrict__ scal, int rz_slot, double *part, unsigned int *count, double *out,
+              const uint8_t *__restrict__ tile_open) {
+    __shared__ float sp[CGY + 2][CGX + 2];
+    const double pq = scal[S_PQ];
+    const double alpha = pq != 0.0 ? scal[rz_slot] / pq : 0.0;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY, ntiles = ntx * nty;
+    const int stride = gridDim.x * gridDim.y;
+    const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
+    constexpr int R = CGY / 4;
+    double v[2] = {0.0, 0.0};
+    int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    uint8_t flag = (tile_open != nullptr && tile < ntiles) ? tile_open[tile] : 0;
+    for (; tile < ntiles; tile += stride) {
+        const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
+        const bool open = flag != 0;                                    // block-uniform
+        if (tile_open != nullptr && tile + stride < ntiles) flag = tile_open[tile + stride];   // in flight during this tile
+        if (open) {
+            const int lane = threadIdx.x & 31;
+            const long idx0 = (long)(F.oj + j0 + R * threadIdx.y - 1) * F.n1 + F.oi + i0 + threadIdx.x;   // row above my first
+            float pn[R + 2], pw[R];
+            double xv[R], rv[R];
+#pragma unroll
+            for (int u = 0; u < R + 2; u++) pn[u] = p[idx0 + (long)u * F.n1];
+#pragma unroll
+            for (int u = 0; u < R; u++) { xv[u] = x[idx0 + (long)(u + 1) * F.n1]; rv[u] = r[idx0 + (long)(u + 1) * F.n1]; }
+            const int side = lane == 0 ? -1 : 1;
+            if (lane == 0 || lane == 31) {
+#pragma unroll
+                for (int u = 0; u < R; u++) pw[u] = p[idx0 + (long)(u + 1) * F.n1 + side];
+            }
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int j = j0 + R * threadIdx.y + u;
+                const float pf = pn[u + 1];
+                float w = __shfl_up_sync(0xffffffffu, pf, 1), e = __shfl_down_sync(0xffffffffu, pf, 1);
+                if (lane == 0) w = pw[u];
+                if (lane == 31) e = pw[u];
+                const double pc = (double)pf;
+                const double qv = cg_q(F, diag_open, pc, (double)w, (double)e, (double)pn[u], (double)pn[u + 2]);
+                const long idx = idx0 + (long)(u + 1) * F.n1;
+                x[idx] = __fma_rn(alpha, pc, xv[u]);
+                const double rn = __fma_rn(-alpha, qv, rv[u]);
+                r[idx] = rn;
+                if (j >= F.jo0 && j < F.jo1) { v[0] = __fma_rn(rn, rn, v[0]); v[1] += rn; }
+            }
+            continue;
+        }
+        __syncthreads();        // the previous masked tile of this CTA is done with sp
+        for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
+            int a = t / (CGX + 2), b = t - a * (CGX + 2);
+            int j = j0 - 1 + a, i = i0 - 1 + b;
+            if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            float pv = 0.0f;
+            long idx;
+            if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF)) pv = p[idx];
+            sp[a][b] = pv;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const int a = 1 + R * threadIdx.y + q, b = 1 + threadIdx.x, j = j0 + R * threadIdx.y + q;   // the open path's thread-to-row map
+            long idx;
+            if (i >= F.nx || j >= F.ny || !fine_index(F, j, i, idx)) continue;
+            uint8_t c = F.nb[idx];
+            if (!(c & NB_SELF)) continue;
+            double cw = (c & NB_W) ? F.cx : 0.0, ce = (c & NB_E) ? F.cx : 0.0;
+            double cs = (c & NB_S) ? F.cy : 0.0, cn = (c & NB_N) ? F.cy : 0.0;
+            const double diag = cg_diag(F, cw, ce, cs, cn);
+            const double pc = (double)sp[a][b];
+            const double qv = cg_q(F, diag, pc, (double)sp[a][b - 1], (double)sp[a][b + 1], (double)sp[a - 1][b], (double)sp[a + 1][b]);
+            x[idx] = __fma_rn(alpha, pc, x[idx]);
+            const double rn = __fma_rn(-alpha, qv, r[idx]);
+            r[idx] = rn;
+            if (j >= F.jo0 && j < F.jo1) { v[0] = __fma_rn(rn, rn, v[0]); v[1] += rn; }
+        }
+    }
+    grid_reduce<OpSum, 2>(v, part, count, out);
+}
+
+// x = sum_k w_k g_k (the first guess, extrapolated from the history of this stage's
+// solutions) and r = f - L x, rr, sum r, ff in ONE pass: the guess is formed once per
+// point of the (64+2) x (16+2) window in shared memory instead of being written by one
+// kernel and read back (with its four neighbours) by the next.  x must not alias a g_k.
+struct GuessW { const double *g[6]; double w[6]; int n; };
+__global__ void __launch_bounds__(256, 4)
+k_cg_resid_guess(FineView F, GuessW G, double *__restrict__ x, const double *__restrict__ f, double fscale,
+                 double *__restrict__ r, double *part, unsigned int *count, double *out,
+                 const uint8_t *__restrict__ tile_open) {
+    __shared__ double sp[CGY + 2][CGX + 2];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY;
     const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
-    double v[1] = {0.0};
+    double v[3] = {0.0, 0.0, 0.0};
+    auto guess_at = [&](long idx) {
+        double a = G.w[0] * G.g[0][idx];
+#pragma unroll
+        for (int m = 1; m < 6; m++)
+            if (m < G.n) a += G.w[m] * G.g[m][idx];
+        return a;
+    };
     for (int tile = blockIdx.y * gridDim.x + blockIdx.x; tile < ntx * nty; tile += gridDim.x * gridDim.y) {
         const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
         const bool open = tile_open != nullptr && tile_open[tile];     // block-uniform
         __syncthreads();
         if (open) {
             const long base = (long)(F.oj + j0 - 1) * F.n1 + F.oi + i0 - 1;
-            constexpr int NW = ((CGY + 2) * (CGX + 2) + 255) / 256;
-            TZ zv[NW];
-            double pv[NW];
-#pragma unroll
-            for (int u = 0; u < NW; u++) {      // every load first
-                int t = tid + u * 256;
+            for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
                 int a = t / (CGX + 2), b = t - a * (CGX + 2);
-                bool in = t < (CGY + 2) * (CGX + 2);
-                long idx = base + (long)a * F.n1 + b;
-                zv[u] = in ? z[idx] : TZ(0);
-                pv[u] = in ? pold[idx] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < NW; u++) {
-                int t = tid + u * 256;
-                if (t < (CGY + 2) * (CGX + 2)) (&sp[0][0])[t] = cg_pnew((double)zv[u], mz, beta, pv[u]);
+                (&sp[0][0])[t] = guess_at(base + (long)a * F.n1 + b);
             }
             __syncthreads();
             const long idx0 = base + (long)(1 + threadIdx.y) * F.n1 + 1 + threadIdx.x;
 #pragma unroll
-            for (int r = 0; r < CGY / 4; r++) {
-                const int a = 1 + threadIdx.y + 4 * r, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * r;
-                const long idx = idx0 + (long)(4 * r) * F.n1;
-                double pc = sp[a][b];
-                double qv = cg_q(F, diag_open, pc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
-                pnew[idx] = pc;
-                q[idx] = qv;
-                if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
+            for (int q = 0; q < CGY / 4; q++) {
+                const int a = 1 + threadIdx.y + 4 * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * q;
+                const long idx = idx0 + (long)(4 * q) * F.n1;
+                const double xc = sp[a][b];
+                const double ff = fscale * f[idx];
+                const double res = ff - cg_q(F, diag_open, xc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
+                x[idx] = xc;
+                r[idx] = res;
+                if (j >= F.jo0 && j < F.jo1) { v[0] += res * res; v[1] += res; v[2] += ff * ff; }
             }
             continue;
         }
@@ -432,34 +625,33 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const double *__restrict__ 
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
             int j = j0 - 1 + a, i = i0 - 1 + b;
             if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
-            double pv = 0.0;
+            double xv = 0.0;
             long idx;
-            if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF))
-                pv = cg_pnew((double)z[idx], mz, beta, pold[idx]);
-            sp[a][b] = pv;
+            if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF)) xv = guess_at(idx);
+            sp[a][b] = xv;
         }
         __syncthreads();
         const int i = i0 + threadIdx.x;
 #pragma unroll
-        for (int r = 0; r < CGY / 4; r++) {
-            const int a = 1 + threadIdx.y + 4 * r, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * r;
+        for (int q = 0; q < CGY / 4; q++) {
+            const int a = 1 + threadIdx.y + 4 * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * q;
             long idx;
             if (i >= F.nx || j >= F.ny || !fine_index(F, j, i, idx)) continue;
             uint8_t c = F.nb[idx];
             if (!(c & NB_SELF)) continue;
             double cw = (c & NB_W) ? F.cx : 0.0, ce = (c & NB_E) ? F.cx : 0.0;
             double cs = (c & NB_S) ? F.cy : 0.0, cn = (c & NB_N) ? F.cy : 0.0;
-            double diag = cg_diag(F, cw, ce, cs, cn);
-            double pc = sp[a][b];
+            const double diag = cg_diag(F, cw, ce, cs, cn);
+            const double xc = sp[a][b];
+            const double ff = fscale * f[idx];
             // closed faces lead to points that are not unknowns: their sp entry is 0
-            double qv = cg_q(F, diag, pc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
-            pnew[idx] = pc;
-            q[idx] = qv;
-            if (j >= F.jo0 && j < F.jo1) v[0] = __fma_rn(pc, qv, v[0]);
+            const double res = ff - cg_q(F, diag, xc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
+            x[idx] = xc;
+            r[idx] = res;
+            if (j >= F.jo0 && j < F.jo1) { v[0] += res * res; v[1] += res; v[2] += ff * ff; }
         }
     }
-    grid_reduce<OpSum, 1>(v, part, count, scal + S_PQ);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) scal[S_RZ0 + (it & 1)] = rznew;
+    grid_reduce<OpSum, 3>(v, part, count, out);
 }
 
 // which tiles of k_cg_dir_apply are open: one CTA per tile
@@ -870,13 +1062,13 @@ static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
 
 void mg_free(f2d_ctx *c, int which) {
     Multigrid &M = c->mg[which];
-    for (cudaGraphExec_t &g : M.gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (Multigrid::IterGraph &g : M.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    M.graphs.clear();
     cudaFree(M.nb);
     cudaFree(M.cg_open); M.cg_open = nullptr;
     cudaFree(M.comp); M.comp = nullptr;
-    for (double *p : {M.r, M.z, M.p, M.q, M.p2}) cudaFree(p);
-    cudaFree(M.zf);
-    cudaFree(M.zf2);
+    for (double *p : {M.r, M.z, M.q}) cudaFree(p);
+    for (float *p : {M.zf, M.zf2, M.p, M.p2}) cudaFree(p);
     for (Level &L : M.lev) {
         for (CT *p : {L.x, L.x2, L.b, L.r, L.cx, L.cy, L.dinv}) cudaFree(p);
         cudaFree(L.mass);
@@ -1091,11 +1283,11 @@ int mg_build(f2d_ctx *c, int which) {
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
         cudaFree(M.lev[l].wall); M.lev[l].wall = nullptr;
     }
-    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2}) {
+    for (double **p : {&M.r, &M.z, &M.q}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
     }
-    for (float **p : {&M.zf, &M.zf2}) {
+    for (float **p : {&M.zf, &M.zf2, &M.p, &M.p2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(float)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(float), c->stream));
     }
@@ -1293,11 +1485,11 @@ static int mg_build_slab(f2d_ctx *c, int which) {
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     free_setup_arrays(M.lev);
     for (Level &L : M.glev) { cudaFree(L.mass); L.mass = nullptr; cudaFree(L.wall); L.wall = nullptr; }
-    for (double **p : {&M.r, &M.z, &M.p, &M.q, &M.p2}) {
+    for (double **p : {&M.r, &M.z, &M.q}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(double)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(double), c->stream));
     }
-    for (float **p : {&M.zf, &M.zf2}) {
+    for (float **p : {&M.zf, &M.zf2, &M.p, &M.p2}) {
         F2D_CUDA(cudaMalloc(p, c->n * sizeof(float)));
         F2D_CUDA(cudaMemsetAsync(*p, 0, c->n * sizeof(float), c->stream));
     }
@@ -1488,6 +1680,15 @@ static dim3 dir_apply_grid(const f2d_ctx *c) {
     static int per_sm = 0;
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_dir_apply<TZ>, 256, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+    }
+    return dim3(c->nsm * per_sm);
+}
+
+static dim3 update_grid(const f2d_ctx *c) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_update_p, 256, 0) != cudaSuccess || per_sm < 1)
             per_sm = 4;
     }
     return dim3(c->nsm * per_sm);
@@ -1783,7 +1984,7 @@ static int zero_unknowns(f2d_ctx *c, const FineView &F, double *x) {
 }
 
 int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, int *iters_out,
-             double *relres_out) {
+             double *relres_out, const GuessSpec *guess) {
     if (which < 0 || which > 2) { set_error("solver id %d", which); return F2D_ERR_ARG; }
     Multigrid &M = c->mg[which];
     if (!M.built) { set_error("solver %d not built (call f2d_set_mask; Helmholtz needs a qg/rsw model)", which); return F2D_ERR_STATE; }
@@ -1806,7 +2007,16 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     bool conv = false;
     auto projected = [&](double rr, double sum) { return singular ? std::max(rr - sum * sum * inv_n, 0.0) : rr; };
 
+    GuessW GW;
+    GW.n = guess ? guess->n : 0;
+    for (int k = 0; k < 6; k++) { GW.g[k] = guess ? guess->g[k] : nullptr; GW.w[k] = guess ? guess->w[k] : 0.0; }
+    for (int k = 0; k < GW.n; k++)
+        if (GW.g[k] == x) { set_error("internal: the first guess reads the array it is written to"); return F2D_ERR_STATE; }
     if (plain) {
+        if (GW.n > 0) {      // x = first guess (the residual this leaves in M.r is not used)
+            k_cg_resid_guess<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
+            LAUNCH_CHECK(c);
+        }
         // plain V-cycle iteration on x itself
         for (it = 0; it <= maxit; it++) {
             k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, nullptr, c->d_part, c->d_count, S + S_RR);
@@ -1837,8 +2047,13 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         auto projected_l = [&](double rr, double sum) { return lazy ? std::max(rr - sum * sum * inv_n, 0.0) : rr; };
         double ff = 0.0;
         // r = b - A x, its norms on the host; returns the relative residual
+        bool first_resid = true;
         auto true_residual = [&](double *rel) -> int {
-            k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
+            if (first_resid && GW.n > 0)      // the first guess is formed on the way
+                k_cg_resid_guess<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
+            else
+                k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
+            first_resid = false;
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_RR, 3, false));
             if (multi) F2D_TRY(project_r(S_RR));
@@ -1849,7 +2064,9 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
             *rel = ff > 0.0 ? std::sqrt(projected_l(c->h_scal[S_RR], c->h_scal[S_SUMR]) / ff) : 0.0;
             return F2D_OK;
         };
-        if (c->dist.on) F2D_TRY(exchange_fine(c, M, x));     // the first guess may come from anywhere
+        // the first guess may come from anywhere; an extrapolated one is formed from arrays whose
+        // ghost rows are current and is itself current on them
+        if (c->dist.on && GW.n == 0) F2D_TRY(exchange_fine(c, M, x));
         F2D_TRY(true_residual(&relres));
         if (ff == 0.0) {   // b == 0: the solution is 0 (up to the Neumann null space)
             F2D_TRY(zero_unknowns(c, F, x));
@@ -1870,14 +2087,14 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         double best = relres;
         static const bool debug = getenv("F2D_DEBUG") != nullptr;
         if (debug) fprintf(stderr, "[f2d] solve %d: initial relres %.3e (%d component%s)\n", which, relres, M.ncomp, M.ncomp > 1 ? "s" : "");
-        double *pold = M.p, *pnew = M.p2;
+        float *pold = M.p, *pnew = M.p2;
         const int slot = lazy ? S_SUMR : -1;   // lazy projection r - mean(r)
         // One iteration = V-cycle + direction/apply + update (+ exchanges and
         // all-reduces): a fixed sequence of ~16 launches.  It is captured once
         // per parity class (first / odd / even iteration: the rz slot and the
         // p ping-pong alternate) into a CUDA graph and replayed, which takes
         // the launch and NCCL enqueue cost off the host.
-        auto iteration = [&](int iter, double *po, double *pn) -> int {
+        auto iteration = [&](int iter, float *po, float *pn) -> int {
             if (unfused) {
                 if (lazy) { k_cg_project<<<nblk, 256, 0, st>>>(F, M.r, S, inv_n); LAUNCH_CHECK(c); }
                 F2D_TRY(vcycle_unfused(c, M, M.z, M.r, 1.0, true));
@@ -1889,7 +2106,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 }
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
-                k_cg_dir_apply<double><<<dir_apply_grid<double>(c), dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, M.q, S, iter, lazy ? 1 : 0, inv_n,
+                k_cg_dir_apply<double><<<dir_apply_grid<double>(c), dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, S, iter, lazy ? 1 : 0, inv_n,
                                                              c->d_part, c->d_count, cg_open);
             } else {
                 F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
@@ -1899,12 +2116,12 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                     k_comp_sub<float><<<nblk, 256, 0, st>>>(F, M.zf2, M.comp, S, CM, -1);
                     LAUNCH_CHECK(c);
                 }
-                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, M.q, S, iter, lazy ? 1 : 0, inv_n,
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, S, iter, lazy ? 1 : 0, inv_n,
                                                             c->d_part, c->d_count, cg_open);
             }
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
-            k_cg_update<<<nblk, 256, 0, st>>>(F, x, M.r, pn, M.q, S, S_RZ0 + (iter & 1), c->d_part, c->d_count, S + S_RR);
+            k_cg_update_p<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, x, M.r, pn, S, S_RZ0 + (iter & 1), c->d_part, c->d_count, S + S_RR, cg_open);
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_RR, 2, false));
             if (multi) F2D_TRY(project_r(S_RR));
@@ -1922,17 +2139,20 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         // CG decides convergence on the residual its recurrence carries.  A solve that
         // needed clearly more iterations than the previous one of the same system is
         // re-checked against the true residual b - A x, and restarted from it if the
-        // recurrence had drifted (at most twice).
-        for (int attempt = 0; attempt < 3; attempt++) {
+        // recurrence had drifted (once: on ill-conditioned grids b - A x itself bottoms out a
+        // few times above the recurrence, and a second restart could not do better).
+        for (int attempt = 0; attempt < 2; attempt++) {
             int k = 0;                                   // iteration within this (re)start
             for (; !conv && it < maxit; it++, k++) {
                 const int cls = k == 0 ? 0 : ((k & 1) ? 1 : 2);
                 if (use_graph) {
-                    if (M.gexec[cls] && M.gx[cls] != x) {       // another x array: re-capture
-                        cudaGraphExecDestroy(M.gexec[cls]);
-                        M.gexec[cls] = nullptr;
-                    }
-                    if (!M.gexec[cls]) {
+                    Multigrid::IterGraph *G = nullptr;
+                    for (Multigrid::IterGraph &g : M.graphs) if (g.x == x && g.cls == cls) { G = &g; break; }
+                    if (!G) {
+                        if (M.graphs.size() >= 96) {            // a caller cycling through many arrays: start over
+                            for (Multigrid::IterGraph &g : M.graphs) cudaGraphExecDestroy(g.exec);
+                            M.graphs.clear();
+                        }
                         cudaGraph_t graph = nullptr;
                         const int64_t l0 = c->launches, e0 = c->exchanges;
                         F2D_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -1940,16 +2160,16 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                         cudaError_t ce = cudaStreamEndCapture(st, &graph);
                         if (rc != F2D_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                         F2D_CUDA(ce);
-                        F2D_CUDA(cudaGraphInstantiate(&M.gexec[cls], graph, 0));
+                        cudaGraphExec_t exec = nullptr;
+                        F2D_CUDA(cudaGraphInstantiate(&exec, graph, 0));
                         cudaGraphDestroy(graph);
-                        M.gx[cls] = x;
-                        M.glaunches[cls] = c->launches - l0;
-                        M.gexchanges[cls] = c->exchanges - e0;
+                        M.graphs.push_back(Multigrid::IterGraph{x, cls, exec, c->launches - l0, c->exchanges - e0});
+                        G = &M.graphs.back();
                         c->launches = l0; c->exchanges = e0;    // counted when the graph runs
                     }
-                    F2D_CUDA(cudaGraphLaunch(M.gexec[cls], st));
-                    c->launches += M.glaunches[cls];
-                    c->exchanges += M.gexchanges[cls];
+                    F2D_CUDA(cudaGraphLaunch(G->exec, st));
+                    c->launches += G->launches;
+                    c->exchanges += G->exchanges;
                 } else {
                     F2D_TRY(iteration(k, pold, pnew));
                 }
@@ -1971,7 +2191,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 best = std::min(best, relres);
                 if (!(relres < 1e6 * best)) { it++; break; }   // diverging: give up, report
             }
-            if (!conv || ff == 0.0 || attempt == 2) break;
+            if (!conv || ff == 0.0 || attempt == 1) break;
             const bool unusual = it > (expected > 0 ? expected + 2 : 12);
             if (!unusual) break;
             double tr = 0.0;
@@ -2056,13 +2276,16 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 *bytes = npts * (1.5 * 8 + 0.5);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.dir_apply") {
-                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, M.q, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count,
+                // R z2 (fp32) p (fp32) bits, W p2 (fp32)
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count,
                                                                             allow_open_tiles() ? M.cg_open : nullptr);
-                *bytes = npts * (4 + 3 * 8 + 1);
+                *bytes = npts * (3 * 4 + 1);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.update") {
-                k_cg_update<<<nblk, 256, 0, c->stream>>>(F, M.z, M.r, M.p, M.q, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP);
-                *bytes = npts * (6 * 8 + 1);
+                // R x r (fp64) p (fp32) bits, W x r
+                k_cg_update_p<<<update_grid(c), dim3(CGX, 4), 0, c->stream>>>(F, M.z, M.r, M.p, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP,
+                                                                            allow_open_tiles() ? M.cg_open : nullptr);
+                *bytes = npts * (4 * 8 + 4 + 1);
                 LAUNCH_CHECK(c);
             } else { set_error("unknown kernel '%s'", name); return F2D_ERR_ARG; }
         }

@@ -267,8 +267,10 @@ k_diag(Grid g, const double *__restrict__ uxin, const double *__restrict__ uyin,
     };
     double ux0 = UX(0, 0), uy0 = UY(0, 0);
     if (PROJECT) { uxo[k_out] = ux0; uyo[k_out] = uy0; }
-    Ux[k_out] = ux0 * g.idx2;
-    Uy[k_out] = uy0 * g.idy2;
+    if (Ux) {           // null: U is formed on demand (ensure_U)
+        Ux[k_out] = ux0 * g.idx2;
+        Uy[k_out] = uy0 * g.idy2;
+    }
     double om = 0;
     if (j >= 1) om = -(ux0 - UX(-s1, 0));
     if (i >= 1) om += uy0 - UY(-1, 0);
@@ -361,8 +363,10 @@ k_diag_tiled(Grid g, const double *__restrict__ uxin, const double *__restrict__
         const double ux0 = sux[a][b], uy0 = suy[a][b];
         uxo[k] = ux0;
         uyo[k] = uy0;
-        Ux[k] = ux0 * g.idx2;
-        Uy[k] = uy0 * g.idy2;
+        if (Ux) {       // null: U is formed on demand (ensure_U)
+            Ux[k] = ux0 * g.idx2;
+            Uy[k] = uy0 * g.idy2;
+        }
         double om = 0.0;
         if (j >= 1) om = -(ux0 - sux[a - 1][b]);
         if (i >= 1) om += uy0 - suy[a][b - 1];
@@ -702,17 +706,6 @@ static int tracer_rhs(f2d_ctx *c, int k) {
 // previous steps by polynomial extrapolation (order = param.solver_guess, as far
 // as the history allows; 0 keeps what x holds).
 // ---------------------------------------------------------------------------
-struct GuessArgs { const double *g[6]; double w[6]; int n; };
-__global__ void __launch_bounds__(256) k_guess(long n, double *__restrict__ x, GuessArgs A) {
-    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double v = A.w[0] * A.g[0][k];
-#pragma unroll
-    for (int m = 1; m < 6; m++)
-        if (m < A.n) v += A.w[m] * A.g[m][k];
-    x[k] = v;
-}
-
 // Polynomial extrapolation in model time through the last `order` solutions of
 // this stage: Lagrange weights for the nodes t_k evaluated at the current step's
 // time (equal steps: the alternating binomials 4, -6, 4, -1 ...).  The pressure
@@ -720,50 +713,93 @@ __global__ void __launch_bounds__(256) k_guess(long n, double *__restrict__ x, G
 // divergence free, only the dt-scaled increment is projected), so with
 // scale_dt the smooth quantity p / dt is what gets extrapolated -- an adaptive
 // dt (model.py:71-87) then costs no accuracy.
-static int guess_before(f2d_ctx *c, int stage, double *x, bool scale_dt) {
+//
+// The solve works IN the history: guess_begin hands out the oldest slot of the
+// stage (one deeper than the extrapolation reads) as the array to solve in, makes
+// the field name point at it, and describes the first guess x0 = sum w_k g_k for the
+// solver's initial-residual kernel to form on the fly (mg.cu: k_cg_resid_guess);
+// guess_end files the slot as the newest entry.  No guess array is written and read
+// back, no solution is copied.
+static int guess_begin(f2d_ctx *c, int stage, const char *field, bool scale_dt, GuessSpec *spec, double **x) {
+    *spec = GuessSpec();
+    *x = c->f(field);
     if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
     GuessHistory &G = c->guess[stage];
-    int order = std::min(G.valid, std::min(c->guess_order, 6));
-    if (order <= 0) return F2D_OK;
-    const double tn = c->sim_t;
-    if (!(tn > G.t[0])) return F2D_OK;        // not a later time (dt <= 0): keep what x holds
-    for (int k = 1; k < order; k++)           // nodes must be strictly ordered in time
-        if (!(G.t[k - 1] > G.t[k])) { order = k; break; }
-    GuessArgs A;
-    A.n = order;
-    for (int k = 0; k < order; k++) {
-        double w = 1.0;
-        for (int m = 0; m < order; m++)
-            if (m != k) w *= (tn - G.t[m]) / (G.t[k] - G.t[m]);
-        if (scale_dt) w *= c->sim_dt / G.dt[k];
-        A.g[k] = G.g[k];
-        A.w[k] = w;
-    }
-    for (int k = order; k < 6; k++) { A.g[k] = nullptr; A.w[k] = 0.0; }
-    long n = (long)c->n;
-    k_guess<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, x, A);
-    LAUNCH_CHECK(c);
-    return F2D_OK;
-}
-
-static int guess_after(f2d_ctx *c, int stage, const double *x) {
-    if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
-    GuessHistory &G = c->guess[stage];
-    const int depth = std::min(c->guess_order, 6);
+    const int depth = std::min(c->guess_order, 6) + 1;
     for (int k = 0; k < depth; k++)
         if (!G.g[k]) {
             F2D_CUDA(cudaMalloc(&G.g[k], c->n * sizeof(double)));
             F2D_CUDA(cudaMemsetAsync(G.g[k], 0, c->n * sizeof(double), c->stream));
         }
-    // rotate: g3 <- g2 <- g1 <- x
+    double *prev = c->f(field);                 // the latest solution of this field, wherever it lives
+    double *slot = G.g[depth - 1];              // oldest entry: not read by the extrapolation below
+    if (slot == prev) {
+        // (only if a caller shrank the history) never solve into the array the guess reads
+        return F2D_OK;
+    }
+    int order = std::min(G.valid, std::min(c->guess_order, 6));
+    const double tn = c->sim_t;
+    if (order > 0 && !(tn > G.t[0])) order = 0;      // not a later time (dt <= 0)
+    for (int k = 1; k < order; k++)                 // nodes must be strictly ordered in time
+        if (!(G.t[k - 1] > G.t[k])) { order = k; break; }
+    if (order > 0) {
+        spec->n = order;
+        for (int k = 0; k < order; k++) {
+            double w = 1.0;
+            for (int m = 0; m < order; m++)
+                if (m != k) w *= (tn - G.t[m]) / (G.t[k] - G.t[m]);
+            if (scale_dt) w *= c->sim_dt / G.dt[k];
+            spec->g[k] = G.g[k];
+            spec->w[k] = w;
+        }
+    } else {                                        // no usable history yet: start from what the field holds
+        spec->n = 1;
+        spec->g[0] = prev;
+        spec->w[0] = 1.0;
+    }
+    if (!c->field_home.count(field)) c->field_home[field] = prev;    // the field's own allocation
+    c->fields[field] = slot;
+    *x = slot;
+    return F2D_OK;
+}
+
+static int guess_end(f2d_ctx *c, int stage, const double *x) {
+    if (stage < 0 || stage >= 3 || c->guess_order <= 0) return F2D_OK;
+    GuessHistory &G = c->guess[stage];
+    const int depth = std::min(c->guess_order, 6) + 1;
+    if (x != G.g[depth - 1]) return F2D_OK;         // guess_begin did not rotate
+    // rotate: the slot just solved in becomes entry 0
     double *last = G.g[depth - 1];
-    for (int k = depth - 1; k > 0; k--) G.g[k] = G.g[k - 1];
-    for (int k = depth - 1; k > 0; k--) { G.t[k] = G.t[k - 1]; G.dt[k] = G.dt[k - 1]; }
+    for (int k = depth - 1; k > 0; k--) { G.g[k] = G.g[k - 1]; G.t[k] = G.t[k - 1]; G.dt[k] = G.dt[k - 1]; }
     G.g[0] = last;
     G.t[0] = c->sim_t;
     G.dt[0] = c->sim_dt;
-    F2D_CUDA(cudaMemcpyAsync(G.g[0], x, c->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    G.valid = std::min(G.valid + 1, 6);
+    G.valid = std::min(G.valid + 1, depth - 1);
+    return F2D_OK;
+}
+
+// U = sharp(u) (operators.py:59-64) for the models that carry the covariant u: the
+// diagnostic kernels no longer store it every stage (16 B per point per stage that
+// nothing on the device reads -- every kernel scales u itself); it is formed when
+// somebody asks for it: a download, f2d_field_ptr, the bulk sums.
+__global__ void __launch_bounds__(256)
+k_sharp(long n, const double *__restrict__ ux, const double *__restrict__ uy, double idx2, double idy2,
+        double *__restrict__ Ux, double *__restrict__ Uy) {
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Ux[k] = ux[k] * idx2;
+    Uy[k] = uy[k] * idy2;
+}
+
+int ensure_U(f2d_ctx *c) {
+    if (!c->U_stale) return F2D_OK;
+    c->U_stale = false;
+    if (!(c->has("u.x") && c->has("U.x"))) return F2D_OK;
+    long n = (long)c->n;
+    k_sharp<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->f("u.x"), c->f("u.y"), c->idx2, c->idy2,
+                                                               c->f("U.x"), c->f("U.y"));
+    c->launches++;
+    F2D_CUDA(cudaGetLastError());
     return F2D_OK;
 }
 
@@ -860,9 +896,11 @@ static int model_rhs_core(f2d_ctx *c, int k) {
         k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, dux, duy, dh, c->m("slip"), c->m("mskv"),
                                                       mf0H, c->f("pv"));
         LAUNCH_CHECK(c);
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi"), false));
-        F2D_TRY(mg_solve(c, F2D_SOLVER_HELMHOLTZ, c->f("pv"), 1.0, c->f("psi"), nullptr, nullptr));
-        F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
+        GuessSpec gs;
+        double *psi;
+        F2D_TRY(guess_begin(c, c->stage_hint, "psi", false, &gs, &psi));
+        F2D_TRY(mg_solve(c, F2D_SOLVER_HELMHOLTZ, c->f("pv"), 1.0, psi, nullptr, nullptr, &gs));
+        F2D_TRY(guess_end(c, c->stage_hint, psi));
         double f0ag = c->cfg.f0 * c->area / c->cfg.g;
         k_qg_back<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("msk"), c->m("mskx"),
                                                         c->m("msky"), c->m("mskv"), f0ag, dux, duy, dh);
@@ -899,7 +937,7 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
     const double *h = c->has("h") ? c->f("h") : nullptr;
     double goa = c->cfg.g / c->area;
 #define DIAG_ARGS g, uxin, uyin, p, h, c->hb, c->m("msk"), c->m("mskx"), c->m("msky"), c->m("slip"), \
-                  c->m("ok.x"), c->m("ok.y"), goa, c->f("u.x"), c->f("u.y"), c->f("U.x"), c->f("U.y"), \
+                  c->m("ok.x"), c->m("ok.y"), goa, c->f("u.x"), c->f("u.y"), (double *)nullptr, (double *)nullptr, \
                   c->f("omega"), c->f("ke"), c->has("p") ? c->f("p") : nullptr
     switch (mk) {
     case -1: k_diag<-1, PROJECT, MODEL><<<grd2d(c), blk2d(), 0, c->stream>>>(DIAG_ARGS); break;
@@ -912,6 +950,7 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
     }
 #undef DIAG_ARGS
     LAUNCH_CHECK(c);
+    c->U_stale = true;          // U = sharp(u) is formed on demand (ensure_U)
     return F2D_OK;
 }
 
@@ -921,7 +960,7 @@ static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin)
     Grid g = grid_of(c);
     dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
 #define TD_ARGS g, uxin, uyin, c->f("p"), c->m("msk"), c->m("mskx"), c->m("msky"), c->m("slip"), c->m("ok.x"), \
-                c->m("ok.y"), c->f("u.x"), c->f("u.y"), c->f("U.x"), c->f("U.y"), c->f("omega"), c->f("ke")
+                c->m("ok.y"), c->f("u.x"), c->f("u.y"), (double *)nullptr, (double *)nullptr, c->f("omega"), c->f("ke")
     switch (c->cfg.innerproduct) {
     case F2D_METHOD_WENO: k_diag_tiled<0><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
     case F2D_METHOD_UPWIND: k_diag_tiled<1><<<grd, blk, 0, c->stream>>>(TD_ARGS); break;
@@ -932,11 +971,12 @@ static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin)
     }
 #undef TD_ARGS
     LAUNCH_CHECK(c);
+    c->U_stale = true;          // U = sharp(u) is formed on demand (ensure_U)
     if (c->cfg.xperiodic) {
         FillMany f;
-        f.n = 6;
-        const char *names[6] = {"u.x", "u.y", "U.x", "U.y", "omega", "ke"};
-        for (int q = 0; q < 6; q++) f.a[q] = c->f(names[q]);
+        f.n = 4;
+        const char *names[4] = {"u.x", "u.y", "omega", "ke"};
+        for (int q = 0; q < 4; q++) f.a[q] = c->f(names[q]);
         int tot = c->n2 * 2 * c->nh;
         k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
         LAUNCH_CHECK(c);
@@ -962,9 +1002,11 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         k_div_u<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->tmp[0], c->tmp[1], c->m("msk"), c->f("div"));
         LAUNCH_CHECK(c);
         // A p = -delta * area       (operators.py:117)
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("p"), true));
-        F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, c->f("p"), nullptr, nullptr));
-        F2D_TRY(guess_after(c, c->stage_hint, c->f("p")));
+        GuessSpec gs;
+        double *pp;
+        F2D_TRY(guess_begin(c, c->stage_hint, "p", true, &gs, &pp));
+        F2D_TRY(mg_solve(c, F2D_SOLVER_CENTERS, c->f("div"), -c->area, pp, nullptr, nullptr, &gs));
+        F2D_TRY(guess_end(c, c->stage_hint, pp));
         F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
         if (c->dist.on) {   // the next tendency reads omega +-3 rows, u and ke +-1
             void *a[4] = {ux, uy, c->f("omega"), c->f("ke")};
@@ -986,9 +1028,11 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         k_c2v<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f(qg ? "pv" : "omega"), c->hb, qg ? c->cfg.f0 / +c->cfg.H : 0.0,
                                                      c->m("mskv"), rhs);
         LAUNCH_CHECK(c);
-        F2D_TRY(guess_before(c, c->stage_hint, c->f("psi"), false));
-        F2D_TRY(mg_solve(c, qg ? F2D_SOLVER_HELMHOLTZ : F2D_SOLVER_VERTICES, rhs, 1.0, c->f("psi"), nullptr, nullptr));
-        F2D_TRY(guess_after(c, c->stage_hint, c->f("psi")));
+        GuessSpec gs;
+        double *psi;
+        F2D_TRY(guess_begin(c, c->stage_hint, "psi", false, &gs, &psi));
+        F2D_TRY(mg_solve(c, qg ? F2D_SOLVER_HELMHOLTZ : F2D_SOLVER_VERTICES, rhs, 1.0, psi, nullptr, nullptr, &gs));
+        F2D_TRY(guess_end(c, c->stage_hint, psi));
         // perpgrad(..., contravariant=True): u.x *= 1/dy**2, u.y *= 1/dx**2
         k_perpgrad<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("psi"), c->m("mskx"), c->m("msky"), c->idy2, c->idx2,
                                                           c->f("U.x"), c->f("U.y"));
@@ -1233,6 +1277,7 @@ int bulk_sums(f2d_ctx *c, int row0, double *out) {
         set_error("bulk diagnostics need ke, omega and U (euler, boussinesq, rsw, qgrsw)");
         return F2D_ERR_UNSUPPORTED;
     }
+    F2D_TRY(ensure_U(c));
     int gs = c->cfg.reserved[1], gn = c->cfg.reserved[2];
     // at an interface the local array is [G ghost rows | owned rows | G ghost rows] with no wall halo on that side
     int j0 = gs > 0 ? gs : 0, j1 = gn > 0 ? c->n2 - gn : c->n2;
@@ -1340,14 +1385,14 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 LAUNCH_CHECK(c);
                 *bytes = npts * (3 * 8 + 1);
             } else if (k == "project_diag") {
-                // R p u.x u.y, W u.x u.y U.x U.y omega ke, masks msk mskx msky slip ok.x ok.y
+                // R p u.x u.y, W u.x u.y omega ke, masks msk mskx msky slip ok.x ok.y
                 F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
-                *bytes = npts * (9 * 8 + 6);
+                *bytes = npts * (7 * 8 + 6);
             } else if (k == "diag" && sw) {
-                // rsw: R u.x u.y h hb, W U.x U.y omega ke p (msk slip ok.x ok.y); qgrsw: R u.x u.y, W U.x U.y omega (slip)
+                // rsw: R u.x u.y h hb, W omega ke p (msk slip ok.x ok.y); qgrsw: R u.x u.y, W omega (slip)
                 if (model == F2D_MODEL_RSW) F2D_TRY((launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct)));
                 else F2D_TRY((launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1)));
-                *bytes = npts * (model == F2D_MODEL_RSW ? 9 * 8 + 4 : 5 * 8 + 1);
+                *bytes = npts * (model == F2D_MODEL_RSW ? 7 * 8 + 4 : 3 * 8 + 1);
             } else if (k == "qg_pv" && model == F2D_MODEL_QGRSW) {
                 // R du.x du.y dh, W pv (slip mskv)
                 k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("ds1.u.x"), c->f("ds1.u.y"), c->f("ds1.h"), c->m("slip"),

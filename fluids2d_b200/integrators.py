@@ -122,8 +122,11 @@ class RKIntegrator:
         skip = {"div", "flx.x", "flx.y", "vomega", "work"} | ({"U.x", "U.y"} if has_u else set())
         # solutions of the step's own elliptic solves: the reference's direct solve
         # overwrites them whatever they hold (elliptic.py:80-87); here they only seed
-        # the iteration, and the device copy of the previous step does that as well
-        if self.param.model in ("euler", "boussinesq"):
+        # the iteration, and after the first step the device copy of the previous
+        # step (and the first-guess history behind it) does that better
+        if not getattr(self, "_seeded", False):
+            pass
+        elif self.param.model in ("euler", "boussinesq"):
             skip |= {"p"}
         elif self.param.model == "qgrsw":
             skip |= {"pv", "psi"}
@@ -146,6 +149,7 @@ class RKIntegrator:
     def step(self, state, time):
         if self.rhs is self._device_rhs:
             self.upload(state, self._step_inputs(state))
+            self._seeded = True
             self._update_forcings(time.t)
             self.engine.step(time.dt, 1)
             self.download(state, self._step_outputs(state))

@@ -166,8 +166,10 @@ int f2d_solver_stats(f2d_ctx *ctx, int64_t *nsolves, int64_t *niters, double *ma
 /* structure of solver `which`: connected components of its unknowns (the
  * all-Neumann operator of elliptic.py:186-190 has one null-space constant per
  * component; each gets its own projection), multigrid levels, and how far the
- * right-hand sides seen so far were from the operator's range:
- * max over solves and components of |sum_c b| / sqrt(N_c b.b) (0 = compatible). */
+ * right-hand sides seen since the last call were from the operator's range:
+ * max over solves and components of |sum_c b| / sqrt(N_c b.b) (0 = compatible; a
+ * right-hand side that is pure rounding noise, e.g. the divergence of an already
+ * projected velocity, reads O(1) and is harmless: it is projected). */
 int f2d_solver_info(f2d_ctx *ctx, int which, int *ncomponents, int *nlevels, double *rhs_incompat);
 
 /* ---- the three kernels of weno.py:412-436, one launch each, flat-index

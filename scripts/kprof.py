@@ -7,7 +7,7 @@ import bench
 import fluids2d_b200 as f2d
 
 f2d.Param._quiet = True
-p = bench.param_for(4096, f2d.Param)
+p = bench.param_for(bench.CONFIGS["euler4096"], 4096, f2d.Param)
 m = f2d.Model(p)
 s = m.state
 s.omega[...] = bench.turbulence_vorticity(m.mesh.x("v"), m.mesh.y("v"), m.mesh.area)

@@ -180,7 +180,10 @@ def test_granular_calls_equal_fused_step():
         b.diag()
     for f in ("u.x", "u.y", "omega", "ke", "p"):
         x, y = a.download(f), b.download(f)
-        assert np.abs(x - y).max() <= 1e-12 * np.abs(y).max(), f   # FMA contraction differs between the fused and the stand-alone update
+        # FMA contraction differs between the fused and the stand-alone update; the two paths also start
+        # their solves from different first guesses (stage history vs the field), so p agrees to the
+        # solver tolerance (rtol 1e-12 of the residual), not to rounding
+        assert np.abs(x - y).max() <= (1e-10 if f == "p" else 1e-12) * np.abs(y).max(), f
 
 
 def test_cfl_reduction_matches_numpy():
