@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "ops.cu", "step.cu", "mg.cu", "dist.cu"]
-HEADERS = ["engine.cuh", "weno.cuh", "reduce.cuh", "mg_tiles.cuh", os.path.join("..", "..", "include", "f2d.h")]
+HEADERS = ["engine.cuh", "weno.cuh", "reduce.cuh", "mg_tiles.cuh", "tma.cuh", os.path.join("..", "..", "include", "f2d.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

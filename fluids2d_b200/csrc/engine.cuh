@@ -177,6 +177,9 @@ struct f2d_ctx {
     // its own allocation, to be handed back / freed
     std::map<std::string, double *> field_home;
     bool U_stale = false;                    // U = sharp(u) is formed on demand (step.cu: ensure_U)
+    // TMA tensor maps (128-byte CUtensorMap blobs) of the (n2,n1) arrays, keyed by (base pointer, box)
+    struct TmaBlob { alignas(64) unsigned char b[128]; bool ok; };
+    std::map<std::pair<const void *, long>, TmaBlob> tma_cache;
     std::vector<std::string> prognostic;     // leaf names, e.g. "u.x","u.y"
     int nstages = 3;
     double *hb = nullptr;                    // topography (zeros by default)

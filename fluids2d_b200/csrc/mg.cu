@@ -400,7 +400,7 @@ __device__ __forceinline__ float cg_pnew32(TZ z, float pold, const CgF32 &K, dou
 }
 
 template <typename TZ>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 6)
 k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ pold,
                float *__restrict__ pnew, double *__restrict__ scal, int it,
                int singular, double inv_n, double *part, unsigned int *count,

@@ -9,10 +9,12 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "engine.cuh"
 #include "reduce.cuh"
 #include "weno.cuh"
+#include "tma.cuh"
 
 namespace f2d {
 
@@ -479,6 +481,126 @@ k_stage_tiled(Grid g, const double *__restrict__ ux, const double *__restrict__ 
             if (NC == 2) { ax = ax + rk.c[1] * rx; ay = ay + rk.c[1] * ry; }
             else {
                 ax = ax + rk.c[1] * rk.dx[1][k]; ay = ay + rk.c[1] * rk.dy[1][k];
+                ax = ax + rk.c[2] * rx; ay = ay + rk.c[2] * ry;
+            }
+        }
+        rk.ubx[k] = sux[a1][b1] + ax;
+        rk.uby[k] = suy[a1][b1] + ay;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The fused tendency + Runge-Kutta update of the projecting models, TMA-fed.
+// One CTA = one 64 x 16 tile of output points.  One elected thread issues four
+// (boussinesq: five) cp.async.bulk.tensor.2d box loads -- omega with its 3-point
+// halo, u.x, u.y, ke (, b) with a 1-point halo -- that land in shared memory and
+// complete on an mbarrier; meanwhile every thread fetches what has no reuse (the
+// stencil-order / mask bytes and the earlier tendencies of its own points) with
+// plain loads.  Box coordinates outside the array are zero-filled by the TMA unit,
+// so the window needs no bounds test.  A thread owns 4 consecutive rows of one
+// column: the y-windows of its points overlap and every neighbour is a
+// shared-memory load at a compile-time offset (no 64-bit address arithmetic per
+// operand, which was a quarter of the instructions of the per-point kernel).
+// 41 KB of shared memory per CTA, 5 CTAs per SM: the loads of the next tiles are
+// in flight while this one computes.  Same expressions, in the same order, as
+// k_rhs_mom: the two agree bit for bit (halo columns are filled afterwards by
+// k_fill_many, as mesh.fill does).
+// ---------------------------------------------------------------------------
+// (the inner box coordinate must be a multiple of 16 bytes -- an even column for fp64,
+//  scripts/tma_probe.cu -- so the boxes start one column further left than the halo needs)
+constexpr int STX = 64, STY = 16, SHO = 3;
+constexpr int SOX = 4, S1X = 2;                              // columns left of the tile in the omega / 1-halo boxes
+constexpr int SOW = STX + 2 * SOX, SOH = STY + 2 * SHO;      // omega box
+constexpr int S1W = STX + 2 * S1X, S1H = STY + 2;            // u.x, u.y, ke, b boxes
+constexpr size_t pad128(size_t n) { return (n + 127) & ~size_t(127); }
+constexpr size_t SOM_BYTES = pad128((size_t)SOW * SOH * 8), S1_BYTES = pad128((size_t)S1W * S1H * 8);
+struct StageMaps { CUtensorMap om, ux, uy, ke, b; };
+
+template <int MV, int MODEL, int NC>
+__global__ void __launch_bounds__(256, 4)
+k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const double *__restrict__ uxg, const double *__restrict__ uyg,
+            const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy, const int8_t *__restrict__ mskx,
+            const int8_t *__restrict__ msky, double halfdy, double *__restrict__ dux, double *__restrict__ duy,
+            RkFuse rk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double(*som)[SOW] = reinterpret_cast<double(*)[SOW]>(smem_raw);
+    double(*sux)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + SOM_BYTES);
+    double(*suy)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + SOM_BYTES + S1_BYTES);
+    double(*ske)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + SOM_BYTES + 2 * S1_BYTES);
+    double(*sbb)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + SOM_BYTES + 3 * S1_BYTES);
+    const int i0 = blockIdx.x * STX, j0 = blockIdx.y * STY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        constexpr unsigned bytes = (unsigned)(SOW * SOH * 8 + (MODEL == M_BOUSS ? 4 : 3) * S1W * S1H * 8);
+        mbar_expect_tx(&bar, bytes);
+        tma_load_2d(&som[0][0], &M.om, i0 - SOX, j0 - SHO, &bar);
+        tma_load_2d(&sux[0][0], &M.ux, i0 - S1X, j0 - 1, &bar);
+        tma_load_2d(&suy[0][0], &M.uy, i0 - S1X, j0 - 1, &bar);
+        tma_load_2d(&ske[0][0], &M.ke, i0 - S1X, j0 - 1, &bar);
+        if (MODEL == M_BOUSS) tma_load_2d(&sbb[0][0], &M.b, i0 - S1X, j0 - 1, &bar);
+    }
+    // ---- per-point operands without reuse: plain loads, in flight with the boxes
+    constexpr int R = STY / 4;
+    const int i = i0 + threadIdx.x;
+    const int jb = j0 + R * threadIdx.y;
+    const long s1 = g.n1;
+    const bool col_ok = i < g.n1;
+    int oxv[R], oyv[R];
+    double mx[R], my[R], d0x[R], d0y[R], d1x[R], d1y[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = jb + r;
+        const bool ok = col_ok && j < g.n2;
+        const long k = ok ? (long)j * s1 + i : 0;
+        oxv[r] = ok ? ovx[k] : 0;
+        oyv[r] = ok ? ovy[k] : 0;
+        mx[r] = ok ? (double)mskx[k] : 0.0;
+        my[r] = ok ? (double)msky[k] : 0.0;
+        d0x[r] = d0y[r] = d1x[r] = d1y[r] = 0.0;
+        if (NC >= 2 && ok) { d0x[r] = rk.dx[0][k]; d0y[r] = rk.dy[0][k]; }
+        if (NC >= 3 && ok) { d1x[r] = rk.dx[1][k]; d1y[r] = rk.dy[1][k]; }
+    }
+    mbar_wait(&bar, 0);
+    if (!col_ok) return;
+    const int b = SOX + threadIdx.x, b1 = S1X + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = jb + r;
+        if (j >= g.n2) break;
+        const int a = SHO + R * threadIdx.y + r, a1 = 1 + R * threadIdx.y + r;
+        const long k = (long)j * s1 + i;
+        double rx = 0, ry = 0;
+        const int oy = oyv[r];
+        if (oy > 0) {   // du.x: V = U.y, s = yshift, s2 = xshift, sign +1
+            double Vm = 0.25 * (((suy[a1][b1] * g.idy2 + suy[a1 + 1][b1] * g.idy2) + suy[a1][b1 - 1] * g.idy2) +
+                                suy[a1 + 1][b1 - 1] * g.idy2);
+            rx = recon<MV>(oy, Vm, som[a - 2][b], som[a - 1][b], som[a][b], som[a + 1][b], som[a + 2][b], som[a + 3][b]) * Vm;
+        }
+        const int ox = oxv[r];
+        if (ox > 0) {   // du.y: V = U.x, s = xshift, s2 = yshift, sign -1
+            double Vm = 0.25 * (((sux[a1][b1] * g.idx2 + sux[a1][b1 + 1] * g.idx2) + sux[a1 - 1][b1] * g.idx2) +
+                                sux[a1 - 1][b1 + 1] * g.idx2);
+            ry = (-recon<MV>(ox, Vm, som[a][b - 2], som[a][b - 1], som[a][b], som[a][b + 1], som[a][b + 2], som[a][b + 3])) * Vm;
+        }
+        if (i >= 1) rx -= (ske[a1][b1] - ske[a1][b1 - 1]) * mx[r];
+        if (j >= 1) ry -= (ske[a1][b1] - ske[a1 - 1][b1]) * my[r];
+        if (MODEL == M_BOUSS) {
+            if (j >= 1) ry += (halfdy * (sbb[a1][b1] + sbb[a1 - 1][b1])) * my[r];
+        }
+        if (rk.write_ds) { dux[k] = rx; duy[k] = ry; }
+        double ax, ay;
+        if (NC == 1) { ax = rk.c[0] * rx; ay = rk.c[0] * ry; }
+        else {
+            ax = rk.c[0] * d0x[r]; ay = rk.c[0] * d0y[r];
+            if (NC == 2) { ax = ax + rk.c[1] * rx; ay = ay + rk.c[1] * ry; }
+            else {
+                ax = ax + rk.c[1] * d1x[r]; ay = ay + rk.c[1] * d1y[r];
                 ax = ax + rk.c[2] * rx; ay = ay + rk.c[2] * ry;
             }
         }
@@ -1077,14 +1199,85 @@ static int rk_coefs(int integ, double dt, int stage, double *co) {
     return 0;
 }
 
+// cached tensor map of an (n2,n1) fp64 field for boxes of bh x bw; false if TMA cannot be used for it
+static bool field_map(f2d_ctx *c, const double *base, int bh, int bw, CUtensorMap *out) {
+    auto key = std::make_pair((const void *)base, (long)bh * 1024 + bw);
+    auto it = c->tma_cache.find(key);
+    if (it == c->tma_cache.end()) {
+        f2d_ctx::TmaBlob blob;
+        static_assert(sizeof(CUtensorMap) == sizeof(blob.b), "CUtensorMap is a 128-byte blob");
+        CUtensorMap m;
+        blob.ok = tma_make_2d(&m, base, 8, c->n2, c->n1, c->n1, bh, bw);
+        memcpy(blob.b, &m, sizeof(m));
+        it = c->tma_cache.emplace(key, blob).first;
+    }
+    if (!it->second.ok) return false;
+    memcpy(out, it->second.b, sizeof(CUtensorMap));
+    return true;
+}
+
+static int fill_stage_outputs(f2d_ctx *c, double *dux, double *duy, const RkFuse &rk) {
+    if (!c->cfg.xperiodic) return F2D_OK;
+    FillMany f;
+    f.n = 0;
+    if (rk.write_ds) { f.a[f.n++] = dux; f.a[f.n++] = duy; }
+    f.a[f.n++] = rk.ubx; f.a[f.n++] = rk.uby;
+    int tot = c->n2 * 2 * c->nh;
+    k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+    LAUNCH_CHECK(c);
+    return F2D_OK;
+}
+
+// F2D_STAGE=tma (default where the arrays qualify: even n1) | point (one thread per point,
+// L1-cached loads: the round-1 kernel) | tiled (its shared-memory variant, kept for study)
+static int stage_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("F2D_STAGE");
+        v = !e ? 0 : (!strcmp(e, "point") ? 1 : (!strcmp(e, "tiled") ? 2 : 0));
+        if (getenv("F2D_TILED_STAGE")) v = 2;
+    }
+    return v;
+}
+
 template <int MODEL, int NC>
 static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse &rk) {
-    // measured on B200 (4096^2): the L1-cached one-thread-per-point kernel
-    // (0.396 ms) beats this shared-memory version (0.456 ms); kept for study
-    static const bool tiled = getenv("F2D_TILED_STAGE") != nullptr;
-    if (!tiled) return launch_rhs_mom<MODEL, NC>(c, dux, duy, rk);
+    const int variant = stage_variant();
     Grid g = grid_of(c);
     const double *b = c->has("b") ? c->f("b") : nullptr;
+    if (variant == 0) {
+        StageMaps M;
+        bool ok = field_map(c, c->f("omega"), SOH, SOW, &M.om) && field_map(c, c->f("u.x"), S1H, S1W, &M.ux) &&
+                  field_map(c, c->f("u.y"), S1H, S1W, &M.uy) && field_map(c, c->f("ke"), S1H, S1W, &M.ke);
+        if (ok && MODEL == M_BOUSS) ok = field_map(c, b, S1H, S1W, &M.b);
+        else if (ok) M.b = M.ke;
+        if (ok) {
+            constexpr size_t smem = SOM_BYTES + (MODEL == M_BOUSS ? 4 : 3) * S1_BYTES;
+            dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
+#define TMA_ARGS M, g, c->f("u.x"), c->f("u.y"), c->m("ov.x"), c->m("ov.y"), c->m("mskx"), c->m("msky"), 0.5 * c->dy, dux, duy, rk
+#define TMA_LAUNCH(MV)                                                                                        \
+    {                                                                                                         \
+        static bool once = false;                                                                             \
+        if (!once) {                                                                                          \
+            F2D_CUDA(cudaFuncSetAttribute(k_stage_tma<MV, MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            once = true;                                                                                      \
+        }                                                                                                     \
+        k_stage_tma<MV, MODEL, NC><<<grd, blk, smem, c->stream>>>(TMA_ARGS);                                  \
+    }
+            switch (c->cfg.vortexforce) {
+            case F2D_METHOD_WENO: TMA_LAUNCH(WENO) break;
+            case F2D_METHOD_UPWIND: TMA_LAUNCH(UPWIND) break;
+            case F2D_METHOD_CENTERED: TMA_LAUNCH(CENTERED) break;
+            case F2D_METHOD_CWENO: TMA_LAUNCH(CWENO) break;
+            default: set_error("bad vortexforce method"); return F2D_ERR_ARG;
+            }
+#undef TMA_LAUNCH
+#undef TMA_ARGS
+            LAUNCH_CHECK(c);
+            return fill_stage_outputs(c, dux, duy, rk);
+        }
+    }
+    if (variant != 2) return launch_rhs_mom<MODEL, NC>(c, dux, duy, rk);
     dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
 #define ST_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"), b, c->m("ov.x"), c->m("ov.y"), \
                 c->m("mskx"), c->m("msky"), 0.5 * c->dy, dux, duy, rk
@@ -1097,16 +1290,7 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
     }
 #undef ST_ARGS
     LAUNCH_CHECK(c);
-    if (c->cfg.xperiodic) {
-        FillMany f;
-        f.n = 0;
-        if (rk.write_ds) { f.a[f.n++] = dux; f.a[f.n++] = duy; }
-        f.a[f.n++] = rk.ubx; f.a[f.n++] = rk.uby;
-        int tot = c->n2 * 2 * c->nh;
-        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
-        LAUNCH_CHECK(c);
-    }
-    return F2D_OK;
+    return fill_stage_outputs(c, dux, duy, rk);
 }
 
 // Euler / Boussinesq stage with the velocity update fused into the tendency

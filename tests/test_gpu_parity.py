@@ -296,3 +296,40 @@ def test_open_tile_path_gives_the_same_bits_as_the_masked_path(tmp_path):
         res[tag] = np.load(path)
     for k in res["open"].files:
         assert np.array_equal(res["open"][k], res["generic"][k]), k
+
+
+_STAGE_SNIPPET = """
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests')
+import numpy as np
+from util import Golden, engine_for
+out = dict()
+for case in ("xper_noslip", "disc_island", "warm_bubble", "lock_exchange", "euler_cweno"):
+    g = Golden(case)
+    e = engine_for(g)
+    for dt in g.dts[:3]:
+        e.step(dt, 1)
+    for f in ("u.x", "u.y", "omega", "ke", "p"):
+        out[case + "/" + f] = e.download(f)
+    e.close()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_tma_stage_kernel_gives_the_same_bits_as_the_per_point_kernel(tmp_path):
+    """step.cu: k_stage_tma (cp.async.bulk.tensor boxes into shared memory, zero-filled
+    outside the array) evaluates the same expressions in the same order as k_rhs_mom
+    (one thread per point, guarded global loads): three steps of closed, masked and
+    x-periodic euler / boussinesq cases must agree bit for bit (F2D_STAGE=point selects
+    the old kernel)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("tma", {}), ("point", {"F2D_STAGE": "point"})):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", _STAGE_SNIPPET.format(root=root), path], check=True,
+                       env={**os.environ, **env}, timeout=600)
+        res[tag] = np.load(path)
+    for k in res["tma"].files:
+        assert np.array_equal(res["tma"][k], res["point"][k]), k
