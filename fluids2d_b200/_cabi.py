@@ -102,7 +102,7 @@ def load(exact=False):
     """dlopen libf2d.so (or libf2d_exact.so); raises if it is not built."""
     key = bool(exact)
     if key not in _libs:
-        path = _build.lib_path(exact)
+        path = os.environ.get("F2D_LIB_PATH") or _build.lib_path(exact)     # F2D_LIB_PATH: a development build to A/B
         if not os.path.exists(path):
             raise F2DError(-1, f"{path} is not built: run `python -m fluids2d_b200.build` "
                                "(nvcc, sm_100a). There is no CPU fallback.")

@@ -359,7 +359,13 @@ k_dot2(FineView F, const double *__restrict__ r, const double *__restrict__ z,
 //   that rounding in the V-cycle cannot feed the null space.
 //   A CTA forms pnew once per point of a (64+2) x (16+2) window in shared
 //   memory and applies the 5-point operator from there.
-constexpr int CGX = 64, CGY = 16;
+#ifndef F2D_CGX
+#define F2D_CGX 64
+#define F2D_CGY 16
+#endif
+constexpr int CGX = F2D_CGX, CGY = F2D_CGY;   // tile of the CG vector kernels: 256 threads as CGX x CGTY, CGY / CGTY rows each
+constexpr int CGTY = 256 / CGX;
+static_assert(CGX % 32 == 0 && 256 % CGX == 0 && CGY % CGTY == 0, "CG tile shape");
 
 // the two expressions both paths of k_cg_dir_apply evaluate, with explicit roundings
 __device__ __forceinline__ double cg_pnew(double z, double mz, double beta, double pold) {
@@ -386,12 +392,17 @@ __device__ __forceinline__ double cg_diag(const FineView &F, double cw, double c
 // of p and alpha only perturbs the conjugacy of successive directions at the 1e-7 level,
 // far below what the 4-5 iterations of a solve can see.
 //
-//   tile_open[tile] != 0 (k_cg_tile_flags): the whole window lies inside the array, needs
-//   no periodic wrap and holds unknowns only -> no mask bytes, no bounds tests, NO shared
+//   tile_open[tile] != 0 (k_cg_tile_flags): the whole window lies inside the array (its W / E
+//   halo column may be the periodic image) and holds unknowns only -> no mask bytes, no bounds tests, NO shared
 //   memory and no barrier: a thread owns 4 consecutive rows of one column, issues all its
 //   loads first, and gets its W / E neighbours from the adjacent lanes (the two edge lanes
 //   of a warp load theirs).  Both paths evaluate the same expressions with the same
 //   thread-to-row map: same bits, whichever tiles are open.
+// flat offset of the W neighbour of a tile's first column / the E neighbour of its last one
+__device__ __forceinline__ void cg_side_offsets(const FineView &F, int i0, long &woff, long &eoff) {
+    woff = (F.periodic && i0 == 0) ? (long)(F.nx - 1) : -1L;
+    eoff = (F.periodic && i0 + CGX == F.nx) ? -(long)(F.nx - 1) : 1L;
+}
 struct CgF32 { float mz, beta; };
 template <typename TZ>
 __device__ __forceinline__ float cg_pnew32(TZ z, float pold, const CgF32 &K, double mz, double beta) {
@@ -415,7 +426,7 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ p
     const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY, ntiles = ntx * nty;
     const int stride = gridDim.x * gridDim.y;
     const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
-    constexpr int R = CGY / 4;
+    constexpr int R = CGY / CGTY;
     double v[1] = {0.0};
     int tile = blockIdx.y * gridDim.x + blockIdx.x;
     uint8_t flag = (tile_open != nullptr && tile < ntiles) ? tile_open[tile] : 0;
@@ -430,7 +441,9 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ p
             float pv[R + 2], pw[R];
 #pragma unroll
             for (int u = 0; u < R + 2; u++) { zv[u] = z[idx0 + (long)u * F.n1]; pv[u] = pold[idx0 + (long)u * F.n1]; }
-            const int side = lane == 0 ? -1 : 1;
+            long woff, eoff;
+            cg_side_offsets(F, i0, woff, eoff);
+            const long side = lane == 0 ? (threadIdx.x == 0 ? woff : -1L) : (threadIdx.x == CGX - 1 ? eoff : 1L);
             if (lane == 0 || lane == 31) {
 #pragma unroll
                 for (int u = 0; u < R; u++) {
@@ -503,7 +516,7 @@ k_cg_update_p(FineView F, double *__restrict__ x, double *__restrict__ r, const 
     const int ntx = (F.nx + CGX - 1) / CGX, nty = (F.ny + CGY - 1) / CGY, ntiles = ntx * nty;
     const int stride = gridDim.x * gridDim.y;
     const double diag_open = cg_diag(F, F.cx, F.cx, F.cy, F.cy);
-    constexpr int R = CGY / 4;
+    constexpr int R = CGY / CGTY;
     double v[2] = {0.0, 0.0};
     int tile = blockIdx.y * gridDim.x + blockIdx.x;
     uint8_t flag = (tile_open != nullptr && tile < ntiles) ? tile_open[tile] : 0;
@@ -520,7 +533,9 @@ k_cg_update_p(FineView F, double *__restrict__ x, double *__restrict__ r, const 
             for (int u = 0; u < R + 2; u++) pn[u] = p[idx0 + (long)u * F.n1];
 #pragma unroll
             for (int u = 0; u < R; u++) { xv[u] = x[idx0 + (long)(u + 1) * F.n1]; rv[u] = r[idx0 + (long)(u + 1) * F.n1]; }
-            const int side = lane == 0 ? -1 : 1;
+            long woff, eoff;
+            cg_side_offsets(F, i0, woff, eoff);
+            const long side = lane == 0 ? (threadIdx.x == 0 ? woff : -1L) : (threadIdx.x == CGX - 1 ? eoff : 1L);
             if (lane == 0 || lane == 31) {
 #pragma unroll
                 for (int u = 0; u < R; u++) pw[u] = p[idx0 + (long)(u + 1) * F.n1 + side];
@@ -602,16 +617,19 @@ k_cg_resid_guess(FineView F, GuessW G, double *__restrict__ x, const double *__r
         __syncthreads();
         if (open) {
             const long base = (long)(F.oj + j0 - 1) * F.n1 + F.oi + i0 - 1;
+            long woff, eoff;
+            cg_side_offsets(F, i0, woff, eoff);
             for (int t = tid; t < (CGY + 2) * (CGX + 2); t += 256) {
                 int a = t / (CGX + 2), b = t - a * (CGX + 2);
-                (&sp[0][0])[t] = guess_at(base + (long)a * F.n1 + b);
+                long col = b == 0 ? 1 + woff : (b == CGX + 1 ? CGX + eoff : (long)b);     // halo columns may wrap
+                (&sp[0][0])[t] = guess_at(base + (long)a * F.n1 + col);
             }
             __syncthreads();
             const long idx0 = base + (long)(1 + threadIdx.y) * F.n1 + 1 + threadIdx.x;
 #pragma unroll
-            for (int q = 0; q < CGY / 4; q++) {
-                const int a = 1 + threadIdx.y + 4 * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * q;
-                const long idx = idx0 + (long)(4 * q) * F.n1;
+            for (int q = 0; q < CGY / CGTY; q++) {
+                const int a = 1 + threadIdx.y + CGTY * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + CGTY * q;
+                const long idx = idx0 + (long)(CGTY * q) * F.n1;
                 const double xc = sp[a][b];
                 const double ff = fscale * f[idx];
                 const double res = ff - cg_q(F, diag_open, xc, sp[a][b - 1], sp[a][b + 1], sp[a - 1][b], sp[a + 1][b]);
@@ -633,8 +651,8 @@ k_cg_resid_guess(FineView F, GuessW G, double *__restrict__ x, const double *__r
         __syncthreads();
         const int i = i0 + threadIdx.x;
 #pragma unroll
-        for (int q = 0; q < CGY / 4; q++) {
-            const int a = 1 + threadIdx.y + 4 * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + 4 * q;
+        for (int q = 0; q < CGY / CGTY; q++) {
+            const int a = 1 + threadIdx.y + CGTY * q, b = 1 + threadIdx.x, j = j0 + threadIdx.y + CGTY * q;
             long idx;
             if (i >= F.nx || j >= F.ny || !fine_index(F, j, i, idx)) continue;
             uint8_t c = F.nb[idx];
@@ -659,13 +677,19 @@ __global__ void __launch_bounds__(256) k_cg_tile_flags(FineView F, uint8_t *__re
     const int ntx = (F.nx + CGX - 1) / CGX;
     const int tile = blockIdx.x;
     const int i0 = (tile % ntx) * CGX, j0 = (tile / ntx) * CGY;
-    int good = j0 - 1 >= 0 && j0 + CGY + 1 <= F.ny && i0 - 1 >= 0 && i0 + CGX + 1 <= F.nx &&
-               F.oj + j0 - 1 >= 0 && F.oj + j0 + CGY + 1 <= F.n2 && F.oi + i0 - 1 >= 0 && F.oi + i0 + CGX + 1 <= F.n1;
+    // x-periodic: the first / last tile of a row takes its W / E halo column from the other end
+    // of the window (cg_side_offsets); everything else must lie inside window and array
+    const bool wl = F.periodic && i0 == 0, wr = F.periodic && i0 + CGX == F.nx;
+    int good = j0 - 1 >= 0 && j0 + CGY + 1 <= F.ny && (wl || i0 - 1 >= 0) && (wr || i0 + CGX + 1 <= F.nx) && i0 + CGX <= F.nx &&
+               F.oj + j0 - 1 >= 0 && F.oj + j0 + CGY + 1 <= F.n2 && F.oi + i0 - (wl ? 0 : 1) >= 0 &&
+               F.oi + i0 + CGX + (wr ? 0 : 1) <= F.n1;
     if (good) {
-        const long base = (long)(F.oj + j0 - 1) * F.n1 + F.oi + i0 - 1;
+        const long row0 = (long)(F.oj + j0 - 1) * F.n1 + F.oi;
         for (int t = threadIdx.x; t < (CGY + 2) * (CGX + 2); t += blockDim.x) {
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
-            if ((F.nb[base + (long)a * F.n1 + b] & 31) != 31) good = 0;    // an unknown with four open faces
+            int i = i0 - 1 + b;
+            if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx;
+            if ((F.nb[row0 + (long)a * F.n1 + i] & 31) != 31) good = 0;    // an unknown with four open faces
         }
     }
     good = __syncthreads_and(good);
@@ -2014,7 +2038,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         if (GW.g[k] == x) { set_error("internal: the first guess reads the array it is written to"); return F2D_ERR_STATE; }
     if (plain) {
         if (GW.n > 0) {      // x = first guess (the residual this leaves in M.r is not used)
-            k_cg_resid_guess<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
+            k_cg_resid_guess<<<update_grid(c), dim3(CGX, CGTY), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
             LAUNCH_CHECK(c);
         }
         // plain V-cycle iteration on x itself
@@ -2050,7 +2074,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
         bool first_resid = true;
         auto true_residual = [&](double *rel) -> int {
             if (first_resid && GW.n > 0)      // the first guess is formed on the way
-                k_cg_resid_guess<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
+                k_cg_resid_guess<<<update_grid(c), dim3(CGX, CGTY), 0, st>>>(F, GW, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR, cg_open);
             else
                 k_cg_resid<<<nblk, 256, 0, st>>>(F, x, b, fscale, M.r, c->d_part, c->d_count, S + S_RR);
             first_resid = false;
@@ -2106,7 +2130,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                 }
                 k_dot2<<<nblk, 256, 0, st>>>(F, M.r, M.z, S, -1, inv_n, c->d_part, c->d_count, S + S_RZNEW);
                 LAUNCH_CHECK(c);
-                k_cg_dir_apply<double><<<dir_apply_grid<double>(c), dim3(CGX, 4), 0, st>>>(F, M.z, po, pn, S, iter, lazy ? 1 : 0, inv_n,
+                k_cg_dir_apply<double><<<dir_apply_grid<double>(c), dim3(CGX, CGTY), 0, st>>>(F, M.z, po, pn, S, iter, lazy ? 1 : 0, inv_n,
                                                              c->d_part, c->d_count, cg_open);
             } else {
                 F2D_TRY((vcycle_fused<float>(c, M, M.zf, nullptr, M.zf2, M.r, 1.0, true, slot, true)));
@@ -2116,12 +2140,12 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
                     k_comp_sub<float><<<nblk, 256, 0, st>>>(F, M.zf2, M.comp, S, CM, -1);
                     LAUNCH_CHECK(c);
                 }
-                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, st>>>(F, M.zf2, po, pn, S, iter, lazy ? 1 : 0, inv_n,
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, CGTY), 0, st>>>(F, M.zf2, po, pn, S, iter, lazy ? 1 : 0, inv_n,
                                                             c->d_part, c->d_count, cg_open);
             }
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_PQ, 1, false));
-            k_cg_update_p<<<update_grid(c), dim3(CGX, 4), 0, st>>>(F, x, M.r, pn, S, S_RZ0 + (iter & 1), c->d_part, c->d_count, S + S_RR, cg_open);
+            k_cg_update_p<<<update_grid(c), dim3(CGX, CGTY), 0, st>>>(F, x, M.r, pn, S, S_RZ0 + (iter & 1), c->d_part, c->d_count, S + S_RR, cg_open);
             LAUNCH_CHECK(c);
             F2D_TRY(dist_allreduce(c, S + S_RR, 2, false));
             if (multi) F2D_TRY(project_r(S_RR));
@@ -2277,13 +2301,13 @@ int bench_mg_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double *b
                 LAUNCH_CHECK(c);
             } else if (k == "cg.dir_apply") {
                 // R z2 (fp32) p (fp32) bits, W p2 (fp32)
-                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, 4), 0, c->stream>>>(F, M.zf2, M.p, M.p2, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count,
+                k_cg_dir_apply<float><<<dir_apply_grid<float>(c), dim3(CGX, CGTY), 0, c->stream>>>(F, M.zf2, M.p, M.p2, c->d_scal + 16, 0, 0, 0.0, c->d_part, c->d_count,
                                                                             allow_open_tiles() ? M.cg_open : nullptr);
                 *bytes = npts * (3 * 4 + 1);
                 LAUNCH_CHECK(c);
             } else if (k == "cg.update") {
                 // R x r (fp64) p (fp32) bits, W x r
-                k_cg_update_p<<<update_grid(c), dim3(CGX, 4), 0, c->stream>>>(F, M.z, M.r, M.p, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP,
+                k_cg_update_p<<<update_grid(c), dim3(CGX, CGTY), 0, c->stream>>>(F, M.z, M.r, M.p, c->d_scal + 16, S_RZ0, c->d_part, c->d_count, c->d_scal + 16 + S_TMP,
                                                                             allow_open_tiles() ? M.cg_open : nullptr);
                 *bytes = npts * (4 * 8 + 4 + 1);
                 LAUNCH_CHECK(c);
