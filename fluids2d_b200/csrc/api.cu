@@ -188,6 +188,8 @@ int f2d_destroy(f2d_ctx *c) {
     }
     if (c->io_stream) cudaStreamDestroy(c->io_stream);
     cudaFree(c->hb);
+    cudaFree(c->smask);
+    cudaFree(c->dmask);
     for (double *t : c->tmp) cudaFree(t);
     cudaFree(c->d_scal);
     cudaFree(c->d_part);

@@ -177,6 +177,12 @@ struct f2d_ctx {
     // its own allocation, to be handed back / freed
     std::map<std::string, double *> field_home;
     bool U_stale = false;                    // U = sharp(u) is formed on demand (step.cu: ensure_U)
+    // mask bits packed for the fused stencil kernels (ops.cu: k_pack_masks), rebuilt by f2d_set_mask:
+    //   smask (n2, n1):        ov.x/2 | ov.y/2 << 2 | mskx << 4 | msky << 5           (stage kernel: 1 B instead of 4)
+    //   dmask (n2, dpitch):    mskx | msky << 1 | msk << 2 | slip << 3 | ok.x/2 << 4 | ok.y/2 << 6
+    //                          (diagnostic kernel: 1 B instead of 6; dpitch = n1 rounded up to 16 so that TMA can fetch boxes)
+    uint8_t *smask = nullptr, *dmask = nullptr;
+    int dpitch = 0;
     // TMA tensor maps (128-byte CUtensorMap blobs) of the (n2,n1) arrays, keyed by (base pointer, box)
     struct TmaBlob { alignas(64) unsigned char b[128]; bool ok; };
     std::map<std::pair<const void *, long>, TmaBlob> tma_cache;

@@ -88,6 +88,25 @@ __global__ void k_orders(const int8_t *__restrict__ msk, const int8_t *__restric
     oky[i] = (int8_t)order_at(msky, n, i, -n1, maxorder);
 }
 
+// one byte per point carrying every mask / stencil-order value a fused kernel needs (engine.cuh)
+__global__ void k_pack_masks(int n2, int n1, int dpitch, const int8_t *__restrict__ msk, const int8_t *__restrict__ mskx,
+                             const int8_t *__restrict__ msky, const int8_t *__restrict__ slip,
+                             const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy,
+                             const int8_t *__restrict__ okx, const int8_t *__restrict__ oky,
+                             uint8_t *__restrict__ smask, uint8_t *__restrict__ dmask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= dpitch) return;
+    uint8_t d = 0;
+    if (i < n1) {
+        size_t k = (size_t)j * n1 + i;
+        smask[k] = (uint8_t)((ovx[k] >> 1) | ((ovy[k] >> 1) << 2) | ((mskx[k] != 0) << 4) | ((msky[k] != 0) << 5));
+        d = (uint8_t)((mskx[k] != 0) | ((msky[k] != 0) << 1) | ((msk[k] != 0) << 2) | ((slip[k] != 0) << 3) |
+                      ((okx[k] >> 1) << 4) | ((oky[k] >> 1) << 6));
+    }
+    dmask[(size_t)j * dpitch + i] = d;
+}
+
 int build_mesh(f2d_ctx *c, const int8_t *h_msk) {
     const int nh = c->nh, n1 = c->n1, n2 = c->n2;
     int8_t *msk = c->m("msk");
@@ -111,6 +130,14 @@ int build_mesh(f2d_ctx *c, const int8_t *h_msk) {
         msk, c->m("mskx"), c->m("msky"), c->m("slip"), c->m("oc.x"), c->m("oc.y"), c->m("ov.x"),
         c->m("ov.y"), c->m("ok.x"), c->m("ok.y"), n, n1, c->cfg.maxorder);
     c->launches += 2;
+    F2D_CUDA(cudaGetLastError());
+    c->dpitch = (n1 + 15) & ~15;
+    if (!c->smask) F2D_CUDA(cudaMalloc(&c->smask, c->n));
+    if (!c->dmask) F2D_CUDA(cudaMalloc(&c->dmask, (size_t)c->dpitch * n2));
+    k_pack_masks<<<dim3((c->dpitch + 127) / 128, n2), 128, 0, c->stream>>>(
+        n2, n1, c->dpitch, msk, c->m("mskx"), c->m("msky"), c->m("slip"), c->m("ov.x"), c->m("ov.y"), c->m("ok.x"),
+        c->m("ok.y"), c->smask, c->dmask);
+    c->launches++;
     F2D_CUDA(cudaGetLastError());
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     c->mesh_ready = true;

@@ -495,7 +495,7 @@ k_stage_tiled(Grid g, const double *__restrict__ ux, const double *__restrict__ 
 // (boussinesq: five) cp.async.bulk.tensor.2d box loads -- omega with its 3-point
 // halo, u.x, u.y, ke (, b) with a 1-point halo -- that land in shared memory and
 // complete on an mbarrier; meanwhile every thread fetches what has no reuse (the
-// stencil-order / mask bytes and the earlier tendencies of its own points) with
+// packed stencil-order / mask byte and the earlier tendencies of its own points) with
 // plain loads.  Box coordinates outside the array are zero-filled by the TMA unit,
 // so the window needs no bounds test.  A thread owns 4 consecutive rows of one
 // column: the y-windows of its points overlap and every neighbour is a
@@ -518,10 +518,8 @@ struct StageMaps { CUtensorMap om, ux, uy, ke, b; };
 
 template <int MV, int MODEL, int NC>
 __global__ void __launch_bounds__(256, 4)
-k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const double *__restrict__ uxg, const double *__restrict__ uyg,
-            const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy, const int8_t *__restrict__ mskx,
-            const int8_t *__restrict__ msky, double halfdy, double *__restrict__ dux, double *__restrict__ duy,
-            RkFuse rk) {
+k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restrict__ smask, double halfdy,
+            double *__restrict__ dux, double *__restrict__ duy, RkFuse rk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     double(*som)[SOW] = reinterpret_cast<double(*)[SOW]>(smem_raw);
@@ -558,10 +556,11 @@ k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const double *__restric
         const int j = jb + r;
         const bool ok = col_ok && j < g.n2;
         const long k = ok ? (long)j * s1 + i : 0;
-        oxv[r] = ok ? ovx[k] : 0;
-        oyv[r] = ok ? ovy[k] : 0;
-        mx[r] = ok ? (double)mskx[k] : 0.0;
-        my[r] = ok ? (double)msky[k] : 0.0;
+        const unsigned m = ok ? smask[k] : 0u;           // ov.x/2 | ov.y/2 << 2 | mskx << 4 | msky << 5
+        oxv[r] = (m & 3u) << 1;
+        oyv[r] = ((m >> 2) & 3u) << 1;
+        mx[r] = (double)((m >> 4) & 1u);
+        my[r] = (double)((m >> 5) & 1u);
         d0x[r] = d0y[r] = d1x[r] = d1y[r] = 0.0;
         if (NC >= 2 && ok) { d0x[r] = rk.dx[0][k]; d0y[r] = rk.dy[0][k]; }
         if (NC >= 3 && ok) { d1x[r] = rk.dx[1][k]; d1y[r] = rk.dy[1][k]; }
@@ -606,6 +605,107 @@ k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const double *__restric
         }
         rk.ubx[k] = sux[a1][b1] + ax;
         rk.uby[k] = suy[a1][b1] + ay;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The projection + diagnostics of the projecting models, TMA-fed (k_diag_tiled's
+// arithmetic, bit for bit).  Boxes: the un-projected u.x, u.y (70 x 21), p (72 x 22)
+// and the packed mask byte (96 x 21, engine.cuh: dmask) of a 64 x 16 tile with the
+// halos the WENO inner product needs.  Phase 1 projects the whole velocity window in
+// place in shared memory (u -= grad p * mask, operators.py:49-53; zero-filled boxes
+// give 0 outside the array, as the guarded loads of k_diag_tiled do); phase 2 forms
+// u, omega, ke of the thread's 4 consecutive rows from it.  38 KB per CTA.
+// ---------------------------------------------------------------------------
+constexpr int DUW = STX + 6, DUH = STY + 5;       // velocity boxes: columns i0-2 .. i0+67, rows j0-2 .. j0+18
+constexpr int DPW = STX + 8, DPH = STY + 6;       // pressure box:   columns i0-4 .. i0+67, rows j0-3 .. j0+18
+constexpr int DMW = STX + 32, DMH = STY + 5;      // mask box:       columns i0-16 .. i0+79, rows j0-2 .. j0+18
+constexpr size_t DU_BYTES = pad128((size_t)DUW * DUH * 8), DP_BYTES = pad128((size_t)DPW * DPH * 8),
+                 DM_BYTES = pad128((size_t)DMW * DMH);
+struct DiagMaps { CUtensorMap ux, uy, p, m; };
+
+template <int MK>
+__global__ void __launch_bounds__(256, 4)
+k_diag_tma(const __grid_constant__ DiagMaps M, Grid g, double *__restrict__ uxo, double *__restrict__ uyo,
+           double *__restrict__ omega, double *__restrict__ ke) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double(*sux)[DUW] = reinterpret_cast<double(*)[DUW]>(smem_raw);
+    double(*suy)[DUW] = reinterpret_cast<double(*)[DUW]>(smem_raw + DU_BYTES);
+    double(*spp)[DPW] = reinterpret_cast<double(*)[DPW]>(smem_raw + 2 * DU_BYTES);
+    uint8_t(*smk)[DMW] = reinterpret_cast<uint8_t(*)[DMW]>(smem_raw + 2 * DU_BYTES + DP_BYTES);
+    const int i0 = blockIdx.x * STX, j0 = blockIdx.y * STY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (unsigned)(2 * DUW * DUH * 8 + DPW * DPH * 8 + DMW * DMH));
+        tma_load_2d(&sux[0][0], &M.ux, i0 - 2, j0 - 2, &bar);
+        tma_load_2d(&suy[0][0], &M.uy, i0 - 2, j0 - 2, &bar);
+        tma_load_2d(&spp[0][0], &M.p, i0 - 4, j0 - 3, &bar);
+        tma_load_2d(&smk[0][0], &M.m, i0 - 16, j0 - 2, &bar);
+    }
+    mbar_wait(&bar, 0);
+    // ---- phase 1: addgrad(p) on the window (operators.py:49-53)
+    for (int t = tid; t < DUW * DUH; t += 256) {
+        const int a = t / DUW, b = t - a * DUW;
+        const int j = j0 - 2 + a, i = i0 - 2 + b;
+        const unsigned m = smk[a][b + 14];
+        const double pc = spp[a + 1][b + 2];
+        if (i >= 1) sux[a][b] -= (pc - spp[a + 1][b + 1]) * (double)(m & 1u);
+        if (j >= 1) suy[a][b] -= (pc - spp[a][b + 2]) * (double)((m >> 1) & 1u);
+    }
+    __syncthreads();
+    // ---- phase 2
+    constexpr int R = STY / 4;
+    const int b = 2 + threadIdx.x, i = i0 + threadIdx.x;
+    if (i >= g.n1) return;
+    const long s1 = g.n1;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int a = 2 + R * threadIdx.y + r, j = j0 + R * threadIdx.y + r;
+        if (j >= g.n2) break;
+        const long k = (long)j * s1 + i;
+        const unsigned m = smk[a][b + 14];
+        const double ux0 = sux[a][b], uy0 = suy[a][b];
+        uxo[k] = ux0;
+        uyo[k] = uy0;
+        double om = 0.0;
+        if (j >= 1) om = -(ux0 - sux[a - 1][b]);
+        if (i >= 1) om += uy0 - suy[a][b - 1];
+        omega[k] = om * (double)((m >> 3) & 1u);
+        const double mskd = (double)((m >> 2) & 1u);
+        double e = 0.0;
+        if (MK == F2D_METHOD_CLASSIC) {
+            if (i <= g.n1 - 2) { double w = sux[a][b + 1]; e = w * (w * g.idx2) + ux0 * (ux0 * g.idx2); }
+            if (j <= g.n2 - 2) { double w = suy[a + 1][b]; e += w * (w * g.idy2) + uy0 * (uy0 * g.idy2); }
+            e *= mskd * 0.25;
+        } else {
+            constexpr int MM = MK > 3 ? 0 : MK;
+            const int ox = (int)((m >> 4) & 3u) << 1;
+            if (ox > 0) {
+                double w3 = sux[a][b + 1];
+                double Um = 0.5 * (ux0 * g.idx2 + w3 * g.idx2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (ox > 2) { w1 = sux[a][b - 1]; w4 = sux[a][b + 2]; }
+                if (ox > 4) { w0 = sux[a][b - 2]; w5 = sux[a][b + 3]; }
+                e += recon<MM>(ox, Um, w0, w1, ux0, w3, w4, w5) * Um;
+            }
+            const int oy = (int)((m >> 6) & 3u) << 1;
+            if (oy > 0) {
+                double w3 = suy[a + 1][b];
+                double Um = 0.5 * (uy0 * g.idy2 + w3 * g.idy2);
+                double w0 = 0, w1 = 0, w4 = 0, w5 = 0;
+                if (oy > 2) { w1 = suy[a - 1][b]; w4 = suy[a + 2][b]; }
+                if (oy > 4) { w0 = suy[a - 2][b]; w5 = suy[a + 3][b]; }
+                e += recon<MM>(oy, Um, w0, w1, uy0, w3, w4, w5) * Um;
+            }
+            e *= mskd * 0.5;
+        }
+        ke[k] = e;
     }
 }
 
@@ -1076,10 +1176,70 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
     return F2D_OK;
 }
 
+static int fill_diag_outputs(f2d_ctx *c) {
+    c->U_stale = true;          // U = sharp(u) is formed on demand (ensure_U)
+    if (c->cfg.xperiodic) {
+        FillMany f;
+        f.n = 4;
+        const char *names[4] = {"u.x", "u.y", "omega", "ke"};
+        for (int q = 0; q < 4; q++) f.a[q] = c->f(names[q]);
+        int tot = c->n2 * 2 * c->nh;
+        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+
+static bool byte_map(f2d_ctx *c, const uint8_t *base, long rows, long pitch, int bh, int bw, CUtensorMap *out) {
+    auto key = std::make_pair((const void *)base, (long)bh * 1024 + bw);
+    auto it = c->tma_cache.find(key);
+    if (it == c->tma_cache.end()) {
+        f2d_ctx::TmaBlob blob;
+        CUtensorMap m;
+        blob.ok = tma_make_2d(&m, base, 1, rows, pitch, pitch, bh, bw);
+        memcpy(blob.b, &m, sizeof(m));
+        it = c->tma_cache.emplace(key, blob).first;
+    }
+    if (!it->second.ok) return false;
+    memcpy(out, it->second.b, sizeof(CUtensorMap));
+    return true;
+}
+
+static int stage_variant();
+static bool field_map(f2d_ctx *c, const double *base, int bh, int bw, CUtensorMap *out);
+
 static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin) {
     static const bool untiled = getenv("F2D_UNTILED_DIAG") != nullptr;
     if (untiled) return launch_diag<true, M_EULER>(c, uxin, uyin, c->cfg.innerproduct);
     Grid g = grid_of(c);
+    if (stage_variant() == 0) {       // TMA-fed (default where the arrays qualify)
+        DiagMaps M;
+        if (field_map(c, uxin, DUH, DUW, &M.ux) && field_map(c, uyin, DUH, DUW, &M.uy) && field_map(c, c->f("p"), DPH, DPW, &M.p) &&
+            byte_map(c, c->dmask, c->n2, c->dpitch, DMH, DMW, &M.m)) {
+            constexpr size_t smem = 2 * DU_BYTES + DP_BYTES + DM_BYTES;
+            dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
+#define DT_LAUNCH(MKV)                                                                                                \
+    {                                                                                                                 \
+        static bool once = false;                                                                                     \
+        if (!once) {                                                                                                  \
+            F2D_CUDA(cudaFuncSetAttribute(k_diag_tma<MKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            once = true;                                                                                              \
+        }                                                                                                             \
+        k_diag_tma<MKV><<<grd, blk, smem, c->stream>>>(M, g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"));   \
+    }
+            switch (c->cfg.innerproduct) {
+            case F2D_METHOD_WENO: DT_LAUNCH(0) break;
+            case F2D_METHOD_UPWIND: DT_LAUNCH(1) break;
+            case F2D_METHOD_CENTERED: DT_LAUNCH(2) break;
+            case F2D_METHOD_CWENO: DT_LAUNCH(3) break;
+            case F2D_METHOD_CLASSIC: DT_LAUNCH(4) break;
+            default: set_error("bad innerproduct method"); return F2D_ERR_ARG;
+            }
+#undef DT_LAUNCH
+            LAUNCH_CHECK(c);
+            return fill_diag_outputs(c);
+        }
+    }
     dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
 #define TD_ARGS g, uxin, uyin, c->f("p"), c->m("msk"), c->m("mskx"), c->m("msky"), c->m("slip"), c->m("ok.x"), \
                 c->m("ok.y"), c->f("u.x"), c->f("u.y"), (double *)nullptr, (double *)nullptr, c->f("omega"), c->f("ke")
@@ -1093,17 +1253,7 @@ static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin)
     }
 #undef TD_ARGS
     LAUNCH_CHECK(c);
-    c->U_stale = true;          // U = sharp(u) is formed on demand (ensure_U)
-    if (c->cfg.xperiodic) {
-        FillMany f;
-        f.n = 4;
-        const char *names[4] = {"u.x", "u.y", "omega", "ke"};
-        for (int q = 0; q < 4; q++) f.a[q] = c->f(names[q]);
-        int tot = c->n2 * 2 * c->nh;
-        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
-        LAUNCH_CHECK(c);
-    }
-    return F2D_OK;
+    return fill_diag_outputs(c);
 }
 
 // `pre`: the un-projected velocity already sits in tmp[0..1] (fused stage kernel)
@@ -1254,7 +1404,7 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
         if (ok) {
             constexpr size_t smem = SOM_BYTES + (MODEL == M_BOUSS ? 4 : 3) * S1_BYTES;
             dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
-#define TMA_ARGS M, g, c->f("u.x"), c->f("u.y"), c->m("ov.x"), c->m("ov.y"), c->m("mskx"), c->m("msky"), 0.5 * c->dy, dux, duy, rk
+#define TMA_ARGS M, g, c->smask, 0.5 * c->dy, dux, duy, rk
 #define TMA_LAUNCH(MV)                                                                                        \
     {                                                                                                         \
         static bool once = false;                                                                             \
@@ -1537,14 +1687,14 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
         for (int r = 0; r < n; r++) {
             if (k == "advection" && proj) {
                 // stage 2 of rk3, fused with the RK update:
-                // R u.x u.y omega ke ds0.x ds0.y [b], W ds1.x ds1.y ub.x ub.y, masks ov.x ov.y mskx msky
+                // R u.x u.y omega ke ds0.x ds0.y [b], W ds1.x ds1.y ub.x ub.y, packed masks (ov.x ov.y mskx msky in 1 byte)
                 RkFuse rk;
                 rk.c[0] = rk.c[1] = rk.c[2] = 0.0;
                 rk.dx[0] = c->f("ds0.u.x"); rk.dy[0] = c->f("ds0.u.y"); rk.dx[1] = rk.dy[1] = nullptr;
                 rk.ubx = c->tmp[0]; rk.uby = c->tmp[1]; rk.write_ds = 1;
                 if (model == F2D_MODEL_EULER) F2D_TRY((launch_stage_tiled<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
                 else F2D_TRY((launch_stage_tiled<M_BOUSS, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
-                *bytes = npts * ((model == F2D_MODEL_EULER ? 10 : 11) * 8 + 4);
+                *bytes = npts * ((model == F2D_MODEL_EULER ? 10 : 11) * 8 + 1);     // one packed mask byte (smask)
             } else if (k == "advection") {
                 // rsw / qgrsw momentum tendency (vortex force + Coriolis [+ grad(ke + p)]), no fused update:
                 // R u.x u.y omega [ke p], W ds.x ds.y, masks ov.x ov.y mskx msky
@@ -1569,9 +1719,9 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 LAUNCH_CHECK(c);
                 *bytes = npts * (3 * 8 + 1);
             } else if (k == "project_diag") {
-                // R p u.x u.y, W u.x u.y omega ke, masks msk mskx msky slip ok.x ok.y
+                // R p u.x u.y, W u.x u.y omega ke, one packed mask byte (dmask)
                 F2D_TRY(launch_diag_tiled(c, c->tmp[0], c->tmp[1]));
-                *bytes = npts * (7 * 8 + 6);
+                *bytes = npts * (7 * 8 + 1);
             } else if (k == "diag" && sw) {
                 // rsw: R u.x u.y h hb, W omega ke p (msk slip ok.x ok.y); qgrsw: R u.x u.y, W omega (slip)
                 if (model == F2D_MODEL_RSW) F2D_TRY((launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct)));
