@@ -37,9 +37,16 @@ def build(f2d, case, rank, nranks, device):
         m.mesh.finalize()
     xv, yv = m.mesh.xy("v")
     s = m.state
-    s.omega[...] = (gaussian(xv, yv, 0.55 * p.Lx, 0.5 * p.Ly, 0.06) - gaussian(xv, yv, 0.45 * p.Lx, 0.5 * p.Ly, 0.06)) \
-        * m.mesh.mskv * m.mesh.area
-    f2d.tools.set_uv_from_omega(m, s.omega, s.u)
+    if case.get("turbulence"):
+        import bench
+        s.omega[...] = bench.turbulence_vorticity(m.mesh.x("v"), m.mesh.y("v"), m.mesh.area) * m.mesh.mskv
+        f2d.tools.set_uv_from_omega(m, s.omega, s.u)
+        s.u.x[...] *= 20.0      # physical speed ~ 1 (bench.py normalises by the measured maximum; a constant
+        s.u.y[...] *= 20.0      # keeps every rank and the single-GPU reference identical): CFL dt ~ 0.5 / nx
+    else:
+        s.omega[...] = (gaussian(xv, yv, 0.55 * p.Lx, 0.5 * p.Ly, 0.06) - gaussian(xv, yv, 0.45 * p.Lx, 0.5 * p.Ly, 0.06)) \
+            * m.mesh.mskv * m.mesh.area
+        f2d.tools.set_uv_from_omega(m, s.omega, s.u)
     if p.model == "boussinesq":
         s.b[...] = (y + 0.1 * gaussian(x, y, 0.5 * p.Lx, 0.45 * p.Ly, 0.08)) * m.mesh.msk
     m.integrator.diag(s)
