@@ -147,7 +147,8 @@ def config_from_param(param, device=0, solver_rtol=0.0, solver_maxit=0, solver_k
         cfg.ny = slab.ny_ctx
         cfg.reserved[1], cfg.reserved[2], cfg.reserved[3] = slab.gs, slab.gn, slab.ny
     cfg.Lx, cfg.Ly = param.Lx, param.Ly
-    cfg.xperiodic, cfg.yperiodic = int(bool(param.xperiodic)), int(bool(param.yperiodic))
+    cfg.xperiodic = int(bool(param.xperiodic))
+    cfg.yperiodic = 2 if getattr(param, "ywrap", False) else int(bool(param.yperiodic))     # 2: true wrap (f2d.h)
     cfg.noslip = _noslip_flags(param.noslip)
     if slab is not None and slab.nranks > 1 and not (cfg.noslip & NOSLIP_ALL):
         if slab.rank > 0:

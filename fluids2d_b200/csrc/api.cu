@@ -77,6 +77,8 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     NEED(cfg->vortexforce >= 0 && cfg->vortexforce <= 3, "unknown vortexforce method");
     NEED(cfg->compflux >= 0 && cfg->compflux <= 3, "unknown compflux method");
     NEED(cfg->innerproduct >= 0 && cfg->innerproduct <= 4, "unknown innerproduct method");
+    NEED(cfg->yperiodic != 2 || cfg->model == F2D_MODEL_EULER || cfg->model == F2D_MODEL_BOUSSINESQ,
+         "a truly periodic y direction (ywrap) is available for the euler and boussinesq models");
     F2D_CUDA(cudaSetDevice(cfg->device));
     f2d_ctx *c = new f2d_ctx();
     c->cfg = *cfg;

@@ -52,6 +52,7 @@ struct FineView {
     int oj, oi;        // array coordinates of logical (0,0); may be negative
     int n2, n1;        // array shape
     int periodic;      // x wraps inside the window
+    int periodic_y;    // y wraps inside the window (param.ywrap: a true periodic direction, SURVEY note Y)
     int dirichlet;     // vertices: fixed diagonal; centres: Neumann
     double cx, cy;     // dy/dx, dx/dy   (elliptic.py:138-139)
     double shift;      // maindiag       (elliptic.py:186-190)
@@ -64,7 +65,7 @@ struct FineView {
 // (J+1)*pitch + I+1.
 struct CoarseView {
     int ny, nx, pitch;
-    int periodic;
+    int periodic, periodic_y;
     int dirichlet;
     int pj_off;
     const CT *cx;         // coupling across the west face of (J,I)
@@ -105,6 +106,8 @@ struct Dist {
 
 struct Multigrid {
     bool built = false;
+    bool singular = false;            // the operator has a null space of constants (all-Neumann, or Dirichlet
+                                      // vertices of a doubly periodic domain without any wall)
     int which = 0;
     FineView fine{};
     uint8_t *nb = nullptr;            // fine bits, (n2,n1)

@@ -54,7 +54,7 @@ struct Stencil {
     long iw, ie, is, in;
 };
 
-__device__ __forceinline__ Stencil fine_stencil(const FineView &F, int i, long idx, uint8_t c) {
+__device__ __forceinline__ Stencil fine_stencil(const FineView &F, int j, int i, long idx, uint8_t c) {
     Stencil s;
     s.cw = (c & NB_W) ? F.cx : 0.0;
     s.ce = (c & NB_E) ? F.cx : 0.0;
@@ -69,6 +69,10 @@ __device__ __forceinline__ Stencil fine_stencil(const FineView &F, int i, long i
     }
     s.is = idx - F.n1;
     s.in = idx + F.n1;
+    if (F.periodic_y) {
+        if (j == 0) s.is = idx + (long)(F.ny - 1) * F.n1;
+        if (j == F.ny - 1) s.in = idx - (long)(F.ny - 1) * F.n1;
+    }
     return s;
 }
 
@@ -104,6 +108,10 @@ __device__ __forceinline__ void coarse_idx(const CoarseView &V, int J, int I, lo
     }
     s = c - V.pitch;
     n = c + V.pitch;
+    if (V.periodic_y) {
+        if (J == 0) s = c + (long)(V.ny - 1) * V.pitch;
+        if (J == V.ny - 1) n = c - (long)(V.ny - 1) * V.pitch;
+    }
 }
 
 // parents of a fine cell (logical j,i): own aggregate (J0,I0) and the next
@@ -126,7 +134,7 @@ k_smooth0(FineView F, double *__restrict__ x, const double *__restrict__ f, doub
     if (!fine_index(F, j, i, idx)) return;
     uint8_t c = F.nb[idx];
     if (!(c & NB_SELF)) return;
-    Stencil s = fine_stencil(F, i, idx, c);
+    Stencil s = fine_stencil(F, j, i, idx, c);
     if (s.diag <= 0.0) return;
     double a = ZERO_GUESS ? 0.0 : fine_offdiag(s, c, x);
     x[idx] = (fscale * f[idx] + a) / s.diag;
@@ -143,7 +151,7 @@ k_resid0(FineView F, const double *__restrict__ x, const double *__restrict__ f,
     if (!fine_index(F, j, i, idx)) return;
     uint8_t c = F.nb[idx];
     if (!(c & NB_SELF)) return;
-    Stencil s = fine_stencil(F, i, idx, c);
+    Stencil s = fine_stencil(F, j, i, idx, c);
     double res = fscale * f[idx] - (s.diag * x[idx] - fine_offdiag(s, c, x));
     r[idx] = res / w16_of(c, F.dirichlet);
 }
@@ -160,6 +168,7 @@ k_restrict0(FineView F, const double *__restrict__ r, CoarseView C, CT *__restri
 #pragma unroll
     for (int a = -1; a <= 2; a++) {
         int j = 2 * J + a;
+        if (F.periodic_y) { if (j < 0) j += F.ny; else if (j >= F.ny) j -= F.ny; }
         if (j < 0 || j >= F.ny) continue;
         double wy = (a == 0 || a == 1) ? 3.0 : 1.0;
 #pragma unroll
@@ -189,6 +198,7 @@ k_prolong0(FineView F, double *__restrict__ x, CoarseView C, const CT *__restric
     int J0, Jn, I0, In;
     parents(j, i, J0, Jn, I0, In);
     if (C.periodic) { if (In < 0) In += C.nx; else if (In >= C.nx) In -= C.nx; }
+    if (C.periodic_y) { if (Jn < 0) Jn += C.ny; else if (Jn >= C.ny) Jn -= C.ny; }
     long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;   // halo rows absorb Jn=-1, ny
     double v = 9.0 * xc[r0 + I0 + 1];
     if (c & NB_PJ) v += 3.0 * xc[rn + I0 + 1];
@@ -213,7 +223,7 @@ k_cg_resid(FineView F, const double *__restrict__ x, const double *__restrict__ 
         if (!fine_index(F, j, i, idx)) continue;
         uint8_t c = F.nb[idx];
         if (!(c & NB_SELF)) continue;
-        Stencil s = fine_stencil(F, i, idx, c);
+        Stencil s = fine_stencil(F, j, i, idx, c);
         double ff = fscale * f[idx];
         double res = ff - (s.diag * x[idx] - fine_offdiag(s, c, x));
         if (r) r[idx] = res;
@@ -300,7 +310,7 @@ k_cg_apply(FineView F, const double *__restrict__ p, double *__restrict__ q, dou
         if (!fine_index(F, j, i, idx)) continue;
         uint8_t c = F.nb[idx];
         if (!(c & NB_SELF)) continue;
-        Stencil s = fine_stencil(F, i, idx, c);
+        Stencil s = fine_stencil(F, j, i, idx, c);
         double pv = p[idx];
         double qv = s.diag * pv - fine_offdiag(s, c, p);
         q[idx] = qv;
@@ -473,6 +483,7 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ p
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
             int j = j0 - 1 + a, i = i0 - 1 + b;
             if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            if (F.periodic_y) { if (j < 0) j += F.ny; else if (j >= F.ny) j -= F.ny; }
             float pv = 0.0f;
             long idx;
             if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF))
@@ -562,6 +573,7 @@ k_cg_update_p(FineView F, double *__restrict__ x, double *__restrict__ r, const 
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
             int j = j0 - 1 + a, i = i0 - 1 + b;
             if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            if (F.periodic_y) { if (j < 0) j += F.ny; else if (j >= F.ny) j -= F.ny; }
             float pv = 0.0f;
             long idx;
             if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF)) pv = p[idx];
@@ -643,6 +655,7 @@ k_cg_resid_guess(FineView F, GuessW G, double *__restrict__ x, const double *__r
             int a = t / (CGX + 2), b = t - a * (CGX + 2);
             int j = j0 - 1 + a, i = i0 - 1 + b;
             if (F.periodic) { if (i < 0) i += F.nx; else if (i >= F.nx) i -= F.nx; }
+            if (F.periodic_y) { if (j < 0) j += F.ny; else if (j >= F.ny) j -= F.ny; }
             double xv = 0.0;
             long idx;
             if (j >= 0 && j < F.ny && i >= 0 && i < F.nx && fine_index(F, j, i, idx) && (F.nb[idx] & NB_SELF)) xv = guess_at(idx);
@@ -706,7 +719,7 @@ k_apply_A(FineView F, const double *__restrict__ x, double *__restrict__ y) {
     if (!fine_index(F, j, i, idx)) return;
     uint8_t c = F.nb[idx];
     if (!(c & NB_SELF)) return;
-    Stencil s = fine_stencil(F, i, idx, c);
+    Stencil s = fine_stencil(F, j, i, idx, c);
     y[idx] = fine_offdiag(s, c, x) - s.diag * x[idx];
 }
 
@@ -752,6 +765,7 @@ k_restrict(CoarseView Vf, const CT *__restrict__ r, CoarseView C, CT *__restrict
 #pragma unroll
     for (int a = -1; a <= 2; a++) {
         int j = 2 * J + a;
+        if (Vf.periodic_y) { if (j < 0) j += Vf.ny; else if (j >= Vf.ny) j -= Vf.ny; }
         if (j < 0 || j >= Vf.ny) continue;
         double wy = (a == 0 || a == 1) ? 3.0 : 1.0;
 #pragma unroll
@@ -777,6 +791,7 @@ k_prolong(CoarseView Vf, CT *__restrict__ x, CoarseView C, const CT *__restrict_
     int J0, Jn, I0, In;
     parents(j, i, J0, Jn, I0, In);
     if (C.periodic) { if (In < 0) In += C.nx; else if (In >= C.nx) In -= C.nx; }
+    if (C.periodic_y) { if (Jn < 0) Jn += C.ny; else if (Jn >= C.ny) Jn -= C.ny; }
     long r0 = (long)(J0 + 1) * C.pitch, rn = (long)(Jn + 1) * C.pitch;
     double v = 9.0 * xc[r0 + I0 + 1];
     if (c & NB_PJ) v += 3.0 * xc[rn + I0 + 1];
@@ -834,8 +849,11 @@ __global__ void k_build_nb(FineView F, const int8_t *__restrict__ sm, uint8_t *_
         }
         if (hw && sm[iw]) c |= NB_W;
         if (he && sm[ie]) c |= NB_E;
-        if (aj > 0 && sm[idx - F.n1]) c |= NB_S;
-        if (aj < F.n2 - 1 && sm[idx + F.n1]) c |= NB_N;
+        const int j = aj - F.oj;
+        if (F.periodic_y && j == 0) { if (sm[idx + (long)(F.ny - 1) * F.n1]) c |= NB_S; }
+        else if (aj > 0 && sm[idx - F.n1]) c |= NB_S;
+        if (F.periodic_y && j == F.ny - 1) { if (sm[idx - (long)(F.ny - 1) * F.n1]) c |= NB_N; }
+        else if (aj < F.n2 - 1 && sm[idx + F.n1]) c |= NB_N;
     }
     nb[idx] = c;
 }
@@ -901,16 +919,17 @@ __global__ void k_coarsen(Level Lf, Level Lc, int periodic, double wallfac, int 
     Lc.code[cc] = fluid ? NB_SELF : 0;
 }
 
-__global__ void k_build_dinv(Level L, int periodic) {
+__global__ void k_build_dinv(Level L, int periodic) {      // periodic: bit 0 = x, bit 1 = y
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= L.nx || J >= L.ny) return;
     long c = (long)(J + 1) * L.pitch + I + 1;
-    long e = c + 1;
-    if (periodic && I == L.nx - 1) e = c - (L.nx - 1);
+    long e = c + 1, n = c + L.pitch;
+    if ((periodic & 1) && I == L.nx - 1) e = c - (L.nx - 1);
+    if ((periodic & 2) && J == L.ny - 1) n = c - (long)(L.ny - 1) * L.pitch;
     double d = 0.0;
     if (L.code[c] & NB_SELF) {
-        double diag = L.cx[c] + L.cx[e] + L.cy[c] + L.cy[c + L.pitch] + L.mass[c] + L.wall[c];
+        double diag = L.cx[c] + L.cx[e] + L.cy[c] + L.cy[n] + L.mass[c] + L.wall[c];
         d = diag > 0.0 ? 1.0 / diag : 0.0;
     }
     L.dinv[c] = d;
@@ -925,12 +944,13 @@ __global__ void k_mark_regular(Level L, int periodic, CT cx0, CT cy0, CT dinv0) 
     int J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= L.nx || J >= L.ny) return;
     long c = (long)(J + 1) * L.pitch + I + 1;
-    long e = c + 1;
-    if (periodic && I == L.nx - 1) e = c - (L.nx - 1);
+    long e = c + 1, n = c + L.pitch;
+    if ((periodic & 1) && I == L.nx - 1) e = c - (L.nx - 1);
     else if (I == L.nx - 1) return;                      // closed domain: no regular east face
+    if ((periodic & 2) && J == L.ny - 1) n = c - (long)(L.ny - 1) * L.pitch;
     uint8_t code = L.code[c];
     if (!(code & NB_SELF)) return;
-    if (L.cx[c] == cx0 && L.cx[e] == cx0 && L.cy[c] == cy0 && L.cy[c + L.pitch] == cy0 && L.dinv[c] == dinv0)
+    if (L.cx[c] == cx0 && L.cx[e] == cx0 && L.cy[c] == cy0 && L.cy[n] == cy0 && L.dinv[c] == dinv0)
         L.code[c] = code | NB_REG;
 }
 
@@ -943,8 +963,9 @@ static void mark_regular(f2d_ctx *c, const FineView &F, std::vector<Level> &lev,
 __device__ __forceinline__ uint8_t parent_bits(int j, int i, const Level &Lc, int periodic, int pj_off) {
     int J0, Jn, I0, In;
     parents(j, i, J0, Jn, I0, In, pj_off);
+    if (periodic & 2) { if (Jn < 0) Jn += Lc.ny; else if (Jn >= Lc.ny) Jn -= Lc.ny; }
     bool jin = Jn >= 0 && Jn < Lc.ny, iin = true;
-    if (periodic) { if (In < 0) In += Lc.nx; else if (In >= Lc.nx) In -= Lc.nx; }
+    if (periodic & 1) { if (In < 0) In += Lc.nx; else if (In >= Lc.nx) In -= Lc.nx; }
     else iin = In >= 0 && In < Lc.nx;
     uint8_t c = 0;
     if (jin && (Lc.code[(long)(Jn + 1) * Lc.pitch + I0 + 1] & NB_SELF)) c |= NB_PJ;
@@ -975,13 +996,14 @@ __global__ void k_parent_bits(Level Lf, Level Lc, int periodic, int pj_off) {
 }
 
 __global__ void k_solver_mask(const int8_t *__restrict__ m, int8_t *__restrict__ sm, int n2, int n1,
-                              int nh, int xper) {
+                              int nh, int xper) {      // xper: bit 0 = x wraps, bit 1 = y wraps: halo columns / rows are images
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y;
     if (i >= n1) return;
     long k = (long)j * n1 + i;
     int8_t v = m[k] != 0;
-    if (xper && (i < nh || i >= n1 - nh)) v = 0;
+    if ((xper & 1) && (i < nh || i >= n1 - nh)) v = 0;
+    if ((xper & 2) && (j < nh || j >= n2 - nh)) v = 0;
     sm[k] = v;
 }
 
@@ -1022,6 +1044,16 @@ static int label_components(const std::vector<int8_t> &h, int n2, int n1, const 
         if (F.periodic && cur1 > cur0 && runs[cur0].i0 <= F.oi && runs[cur1 - 1].i1 >= F.oi + F.nx)
             unite(runs[cur0].lab, runs[cur1 - 1].lab);
         prev0 = cur0; prev1 = cur1;
+    }
+    if (F.periodic_y && n2 > 0) {     // rows oj and oj + ny - 1 are neighbours
+        std::vector<const Run *> first, last;
+        for (const Run &r : runs) {
+            if (r.j == F.oj) first.push_back(&r);
+            else if (r.j == F.oj + F.ny - 1) last.push_back(&r);
+        }
+        for (const Run *a : first)
+            for (const Run *b : last)
+                if (a->i0 < b->i1 && b->i0 < a->i1) unite(a->lab, b->lab);
     }
     std::vector<int64_t> cnt(parent.size(), 0);
     std::vector<char> open(parent.size(), 0);
@@ -1075,9 +1107,9 @@ static void mark_regular(f2d_ctx *c, const FineView &F, std::vector<Level> &lev,
     }
 }
 
-static CoarseView view_of(const Level &L, int periodic, int dirichlet) {
+static CoarseView view_of(const Level &L, int periodic, int dirichlet, int periodic_y = 0) {
     CoarseView V;
-    V.ny = L.ny; V.nx = L.nx; V.pitch = L.pitch; V.periodic = periodic;
+    V.ny = L.ny; V.nx = L.nx; V.pitch = L.pitch; V.periodic = periodic; V.periodic_y = periodic_y;
     V.cx = L.cx; V.cy = L.cy; V.dinv = L.dinv; V.code = L.code;
     V.dirichlet = dirichlet;
     V.pj_off = 0;
@@ -1161,13 +1193,15 @@ int mg_build(f2d_ctx *c, int which) {
     M.which = which;
     const int n1 = c->n1, n2 = c->n2, nh = c->nh;
     const int xper = c->cfg.xperiodic;
+    const int yper = c->cfg.yperiodic == 2;      // param.ywrap: a true periodic direction (not the reference's mask-only quirk)
+    const int per = xper | (yper << 1);          // what the set-up kernels take: bit 0 = x wraps, bit 1 = y wraps
     const bool vert = which != F2D_SOLVER_CENTERS;
 
     // solver mask and its bounding box
     int8_t *sm;
     F2D_CUDA(cudaMalloc(&sm, c->n));
     k_solver_mask<<<dim3((n1 + 127) / 128, n2), 128, 0, c->stream>>>(c->m(vert ? "mskv" : "msk"), sm,
-                                                                      n2, n1, nh, xper);
+                                                                      n2, n1, nh, per);
     LAUNCH_CHECK(c);
     std::vector<int8_t> h(c->n);
     F2D_CUDA(cudaMemcpyAsync(h.data(), sm, c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -1184,7 +1218,7 @@ int mg_build(f2d_ctx *c, int which) {
     M.nunknown = cnt;
     M.n_global = (double)cnt;
     FineView &F = M.fine;
-    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.dirichlet = vert;
+    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.periodic_y = yper; F.dirichlet = vert;
     F.cx = c->dy / c->dx; F.cy = c->dx / c->dy;
     F.shift = (which == F2D_SOLVER_HELMHOLTZ) ? c->area * c->cfg.f0 * c->cfg.f0 / (c->cfg.g * c->cfg.H) : 0.0;
     if (cnt == 0) {
@@ -1202,8 +1236,8 @@ int mg_build(f2d_ctx *c, int which) {
         while (o > lo) { o = nh - span; span *= 2; }
         return o;
     };
-    F.oj = origin(jmin);
-    F.ny = jmax + 1 - F.oj;
+    if (yper) { F.oj = nh; F.ny = c->cfg.ny; }
+    else { F.oj = origin(jmin); F.ny = jmax + 1 - F.oj; }
     F.jo0 = 0; F.jo1 = F.ny; F.pj_off = 0;
     if (xper) { F.oi = nh; F.nx = c->cfg.nx; }
     else { F.oi = origin(imin); F.nx = imax + 1 - F.oi; }
@@ -1219,7 +1253,10 @@ int mg_build(f2d_ctx *c, int which) {
     }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(sm);
-    if (!vert && F.shift == 0.0) {   // singular operator: one null-space constant per connected component
+    // the operator has constants in its null space: all-Neumann centres; Dirichlet vertices only when the
+    // domain is periodic both ways and has no wall at all (every vertex an unknown)
+    M.singular = F.shift == 0.0 && (!vert || (xper && yper && cnt == (int64_t)F.ny * F.nx));
+    if (!vert && F.shift == 0.0) {   // one null-space constant per connected component
         std::vector<uint8_t> comp;
         std::vector<int64_t> sizes;
         M.ncomp = label_components(h, n2, n1, F, &comp, &sizes);
@@ -1237,15 +1274,16 @@ int mg_build(f2d_ctx *c, int which) {
         int ny = sizes.back().first, nx = sizes.back().second;
         if ((long)ny * nx <= 16 || sizes.size() >= 24) break;
         if (xper && (nx & 1)) break;
+        if (yper && (ny & 1)) break;
         if (ny == 1 && nx == 1) break;
-        sizes.push_back({(ny + 1) / 2, xper ? nx / 2 : (nx + 1) / 2});
+        sizes.push_back({yper ? ny / 2 : (ny + 1) / 2, xper ? nx / 2 : (nx + 1) / 2});
     }
     if (sizes.size() < 2) {
-        if (xper && (F.nx & 1)) {
-            set_error("x-periodic elliptic solve needs an even nx (got %d)", F.nx);
+        if ((xper && (F.nx & 1)) || (yper && (F.ny & 1))) {
+            set_error("a periodic elliptic solve needs an even number of points in that direction (got %d x %d)", F.ny, F.nx);
             return F2D_ERR_UNSUPPORTED;
         }
-        sizes.push_back({(F.ny + 1) / 2, xper ? F.nx / 2 : (F.nx + 1) / 2});
+        sizes.push_back({yper ? F.ny / 2 : (F.ny + 1) / 2, xper ? F.nx / 2 : (F.nx + 1) / 2});
     }
     M.lev.resize(sizes.size());
     for (size_t l = 1; l < sizes.size(); l++) {
@@ -1282,26 +1320,26 @@ int mg_build(f2d_ctx *c, int which) {
         if (need(M.tail) > 200 * 1024) { set_error("coarsest multigrid level too large (%d x %d)", M.lev.back().ny, M.lev.back().nx); return F2D_ERR_UNSUPPORTED; }
     }
     // coefficients, level by level
-    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], xper, 2.0 / 3.0, 0);
+    k_coarsen0<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(F, M.lev[1], per, 2.0 / 3.0, 0);
     LAUNCH_CHECK(c);
-    k_build_dinv<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(M.lev[1], xper);
+    k_build_dinv<<<grd(M.lev[1].nx, M.lev[1].ny), blk(), 0, c->stream>>>(M.lev[1], per);
     LAUNCH_CHECK(c);
     for (size_t l = 1; l + 1 < M.lev.size(); l++) {
         Level &Lc = M.lev[l + 1];
         double pw = std::ldexp(1.0, (int)l);   // 2^l, producing level l+1
-        k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.lev[l], Lc, xper, (pw + 1.0) / (2.0 * pw + 1.0), 0);
+        k_coarsen<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(M.lev[l], Lc, per, (pw + 1.0) / (2.0 * pw + 1.0), 0);
         LAUNCH_CHECK(c);
-        k_build_dinv<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(Lc, xper);
+        k_build_dinv<<<grd(Lc.nx, Lc.ny), blk(), 0, c->stream>>>(Lc, per);
         LAUNCH_CHECK(c);
     }
     // prolongation weights
-    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], xper, 0);
+    k_parent_bits0<<<grd(F.nx, F.ny), blk(), 0, c->stream>>>(F, M.nb, M.lev[1], per, 0);
     LAUNCH_CHECK(c);
     for (size_t l = 1; l + 1 < M.lev.size(); l++) {
-        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], xper, 0);
+        k_parent_bits<<<grd(M.lev[l].nx, M.lev[l].ny), blk(), 0, c->stream>>>(M.lev[l], M.lev[l + 1], per, 0);
         LAUNCH_CHECK(c);
     }
-    if (M.tail > 1) { mark_regular(c, F, M.lev, 1, M.tail - 1, 1, xper); LAUNCH_CHECK(c); }
+    if (M.tail > 1) { mark_regular(c, F, M.lev, 1, M.tail - 1, 1, per); LAUNCH_CHECK(c); }
     F2D_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t l = 1; l < M.lev.size(); l++) {   // set-up only arrays
         cudaFree(M.lev[l].mass); M.lev[l].mass = nullptr;
@@ -1358,9 +1396,10 @@ static int mg_build_slab(f2d_ctx *c, int which) {
     F2D_CUDA(cudaStreamSynchronize(c->stream));
 
     FineView &F = M.fine;
-    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.dirichlet = vert;
+    F.n2 = n2; F.n1 = n1; F.periodic = xper; F.periodic_y = 0; F.dirichlet = vert;
     F.cx = c->dy / c->dx; F.cy = c->dx / c->dy;
     F.shift = (which == F2D_SOLVER_HELMHOLTZ) ? c->area * c->cfg.f0 * c->cfg.f0 / (c->cfg.g * c->cfg.H) : 0.0;
+    M.singular = !vert && F.shift == 0.0;
     F.oj = D.south ? 0 : nh;
     F.ny = (D.north ? n2 : n2 - nh) - F.oj;
     F.oi = nh; F.nx = c->cfg.nx;
@@ -1554,13 +1593,18 @@ __device__ __forceinline__ TailSm tail_sm(CT *sm, const TailLevel &L) {
     return TailSm{p, p + n, p + 2 * n, p + 3 * n, p + 4 * n, p + 5 * n, p + 6 * n};
 }
 
+// periodic: bit 0 = x wraps, bit 1 = y wraps
 __device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const TailSm &S, int periodic, int J, int I) {
-    int s = (J + 1) * L.sp + I + 1, w = s - 1, e = s + 1;
-    if (periodic) {
+    int s = (J + 1) * L.sp + I + 1, w = s - 1, e = s + 1, so = s - L.sp, no = s + L.sp;
+    if (periodic & 1) {
         if (I == 0) w = s + (L.nx - 1);
         if (I == L.nx - 1) e = s - (L.nx - 1);
     }
-    return S.cx[s] * S.x[w] + S.cx[e] * S.x[e] + S.cy[s] * S.x[s - L.sp] + S.cy[s + L.sp] * S.x[s + L.sp];
+    if (periodic & 2) {
+        if (J == 0) so = s + (L.ny - 1) * L.sp;
+        if (J == L.ny - 1) no = s - (L.ny - 1) * L.sp;
+    }
+    return S.cx[s] * S.x[w] + S.cx[e] * S.x[e] + S.cy[s] * S.x[so] + S.cy[no] * S.x[no];
 }
 
 __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
@@ -1628,12 +1672,13 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
 #pragma unroll
             for (int a = -1; a <= 2; a++) {
                 int j = 2 * J + a;
+                if (per & 2) { if (j < 0) j += L.ny; else if (j >= L.ny) j -= L.ny; }
                 if (j < 0 || j >= L.ny) continue;
                 CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
 #pragma unroll
                 for (int b = -1; b <= 2; b++) {
                     int i = 2 * I + b;
-                    if (per) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
+                    if (per & 1) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
                     if (i < 0 || i >= L.nx) continue;
                     CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
                     acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
@@ -1659,7 +1704,8 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
             if (S.dinv[sidx] == CT(0)) continue;      // not an unknown (set-up clears the code where 1/diag is 0)
             int J0, Jn, I0, In;
             parents(J, I, J0, Jn, I0, In);
-            if (per) In = wrap_mod(In, C.nx);
+            if (per & 1) In = wrap_mod(In, C.nx);
+            if (per & 2) Jn = wrap_mod(Jn, C.ny);
             int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
             CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
             S.x[sidx] += v / S.w[sidx];
@@ -1686,9 +1732,9 @@ static int set_smem(K kernel, size_t bytes) {
     return F2D_OK;
 }
 
-static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, int pj_off) {
+static CoarseArrays<CT> arrays_of(const Level &L, int periodic, int dirichlet, int pj_off, int periodic_y) {
     CoarseArrays<CT> A;
-    A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.dirichlet = dirichlet; A.pj_off = pj_off;
+    A.ny = L.ny; A.nx = L.nx; A.pitch = L.pitch; A.periodic = periodic; A.periodic_y = periodic_y; A.dirichlet = dirichlet; A.pj_off = pj_off;
     A.cx = L.cx; A.cy = L.cy; A.dinv = L.dinv; A.code = L.code;
     A.cx0 = L.cx0; A.cy0 = L.cy0; A.dinv0 = L.dinv0;
     return A;
@@ -1757,7 +1803,7 @@ static int launch_up0(f2d_ctx *c, Multigrid &M, const FT *xin, FT *xout, const d
     if (DOT && (size_t)g.x * g.y * 2 > c->part_capacity) { set_error("reduction scratch too small"); return F2D_ERR_STATE; }
     const Level &C = M.lev[1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, xin, xout, f, fscale, c->d_scal, sumr_slot, 1.0 / M.n_global,
-                                               UpArgs{C.ny, C.nx, C.pitch, F.periodic, allow_open_tiles()},
+                                               UpArgs{C.ny, C.nx, C.pitch, F.periodic, allow_open_tiles(), F.periodic_y},
                                                level_result(M, 1), c->d_part, c->d_count, c->d_scal + S_RZNEW);
     LAUNCH_CHECK(c);
     if (DOT) {
@@ -1771,7 +1817,7 @@ template <int NU, int WJ>
 static int launch_down(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_down(NU, true), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
-    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off, M.fine.periodic_y)};
     auto kern = k_mg_down<CT, CT, CT, CT, false, true, NU, WJ, CoarseLevel<CT>>;
     size_t smem = Window<CT, false, WJ>::bytes();
     static bool once = false;
@@ -1788,7 +1834,7 @@ template <int NU, int WJ>
 static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     constexpr int H = halo_up(NU), TJ = WJ - 2 * H, TI = TW - 2 * H;
     Level &Lv = M.lev[l];
-    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off)};
+    CoarseLevel<CT> L{arrays_of(Lv, M.fine.periodic, M.fine.dirichlet, M.fine.pj_off, M.fine.periodic_y)};
     auto kern = k_mg_up<CT, CT, CT, CT, false, false, NU, WJ, CoarseLevel<CT>>;
     size_t smem = ((Window<CT, false, WJ>::bytes() + 15) & ~size_t(15)) + (WJ / 2 + 3) * (TW / 2 + 3) * sizeof(CT);
     static bool once = false;
@@ -1796,7 +1842,7 @@ static int launch_up(f2d_ctx *c, Multigrid &M, int l) {
     dim3 g((Lv.nx + TI - 1) / TI, (Lv.ny + TJ - 1) / TJ);
     const Level &C = M.lev[l + 1];
     kern<<<g, TILE_THREADS, smem, c->stream>>>(L, Lv.x, Lv.x2, Lv.b, 1.0, c->d_scal, -1, 0.0,
-                                               UpArgs{C.ny, C.nx, C.pitch, M.fine.periodic, allow_open_tiles()}, level_result(M, l + 1),
+                                               UpArgs{C.ny, C.nx, C.pitch, M.fine.periodic, allow_open_tiles(), M.fine.periodic_y}, level_result(M, l + 1),
                                                nullptr, nullptr, nullptr);
     LAUNCH_CHECK(c);
     return F2D_OK;
@@ -1831,7 +1877,7 @@ static int launch_tail(f2d_ctx *c, Multigrid &M) {
     const int first = slab ? 0 : M.tail;
     const int nlev = (int)TL.size();
     A.nlev = nlev - first;
-    A.periodic = M.fine.periodic; A.dirichlet = M.fine.dirichlet;
+    A.periodic = M.fine.periodic | (M.fine.periodic_y << 1); A.dirichlet = M.fine.dirichlet;
     A.nu1 = c->cfg.nu1 > 0 ? c->cfg.nu1 : 2;
     A.nu2 = c->cfg.nu2 > 0 ? c->cfg.nu2 : 2;
     const Level &last = TL[nlev - 1];
@@ -1943,13 +1989,13 @@ static int vcycle_unfused(f2d_ctx *c, Multigrid &M, double *x, const double *f, 
     k_resid0<<<g0, blk(), 0, st>>>(F, x, f, fscale, M.q);
     LAUNCH_CHECK(c);
     {
-        CoarseView C1 = view_of(M.lev[1], xper, F.dirichlet);
+        CoarseView C1 = view_of(M.lev[1], xper, F.dirichlet, F.periodic_y);
         k_restrict0<<<grd(C1.nx, C1.ny), blk(), 0, st>>>(F, M.q, C1, M.lev[1].b);
         LAUNCH_CHECK(c);
     }
     for (int l = 1; l < nlev - 1; l++) {
         Level &L = M.lev[l];
-        CoarseView V = view_of(L, xper, F.dirichlet);
+        CoarseView V = view_of(L, xper, F.dirichlet, F.periodic_y);
         dim3 g = grd(L.nx, L.ny);
         F2D_CUDA(cudaMemsetAsync(L.x, 0, L.n * sizeof(CT), st));
         for (int s = 0; s < nu1; s++)
@@ -1960,21 +2006,21 @@ static int vcycle_unfused(f2d_ctx *c, Multigrid &M, double *x, const double *f, 
             }
         k_resid<<<g, blk(), 0, st>>>(V, L.x, L.b, L.r);
         LAUNCH_CHECK(c);
-        CoarseView C = view_of(M.lev[l + 1], xper, F.dirichlet);
+        CoarseView C = view_of(M.lev[l + 1], xper, F.dirichlet, F.periodic_y);
         k_restrict<<<grd(C.nx, C.ny), blk(), 0, st>>>(V, L.r, C, M.lev[l + 1].b);
         LAUNCH_CHECK(c);
     }
     {
         Level &L = M.lev[nlev - 1];
         int npts = L.ny * L.nx;
-        k_coarsest<<<1, 1024, 0, st>>>(view_of(L, xper, F.dirichlet), L.x, L.b, npts <= 64 ? 8 : 24);
+        k_coarsest<<<1, 1024, 0, st>>>(view_of(L, xper, F.dirichlet, F.periodic_y), L.x, L.b, npts <= 64 ? 8 : 24);
         LAUNCH_CHECK(c);
     }
     for (int l = nlev - 2; l >= 1; l--) {
         Level &L = M.lev[l];
-        CoarseView V = view_of(L, xper, F.dirichlet);
+        CoarseView V = view_of(L, xper, F.dirichlet, F.periodic_y);
         dim3 g = grd(L.nx, L.ny);
-        k_prolong<<<g, blk(), 0, st>>>(V, L.x, view_of(M.lev[l + 1], xper, F.dirichlet), M.lev[l + 1].x);
+        k_prolong<<<g, blk(), 0, st>>>(V, L.x, view_of(M.lev[l + 1], xper, F.dirichlet, F.periodic_y), M.lev[l + 1].x);
         LAUNCH_CHECK(c);
         for (int s = 0; s < nu2; s++)
             for (int col = 1; col >= 0; col--) {
@@ -1982,7 +2028,7 @@ static int vcycle_unfused(f2d_ctx *c, Multigrid &M, double *x, const double *f, 
                 LAUNCH_CHECK(c);
             }
     }
-    k_prolong0<<<g0, blk(), 0, st>>>(F, x, view_of(M.lev[1], xper, F.dirichlet), M.lev[1].x);
+    k_prolong0<<<g0, blk(), 0, st>>>(F, x, view_of(M.lev[1], xper, F.dirichlet, F.periodic_y), M.lev[1].x);
     LAUNCH_CHECK(c);
     for (int s = 0; s < nu2; s++)
         for (int col = 1; col >= 0; col--) {
@@ -2022,7 +2068,7 @@ int mg_solve(f2d_ctx *c, int which, const double *b, double bscale, double *x, i
     const double fscale = -bscale;   // L = -A
     const dim3 nblk = cg_grid(c, F);
     const uint8_t *cg_open = allow_open_tiles() ? M.cg_open : nullptr;
-    const bool singular = !F.dirichlet && F.shift == 0.0;
+    const bool singular = M.singular;
     const bool plain = (c->cfg.solver_kind & 1) != 0, unfused = (c->cfg.solver_kind & 2) != 0;
     const double N = M.n_global, inv_n = 1.0 / N;
     double *S = c->d_scal;

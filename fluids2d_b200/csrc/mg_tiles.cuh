@@ -57,7 +57,7 @@ __host__ __device__ constexpr int halo_up(int nu) { return 2 * nu; }
 
 template <typename T>
 struct CoarseArrays {       // level l >= 1, halo-padded (ny+2) x pitch
-    int ny, nx, pitch, periodic, dirichlet, pj_off;
+    int ny, nx, pitch, periodic, periodic_y, dirichlet, pj_off;
     const T *cx, *cy, *dinv;
     const uint8_t *code;
     T cx0, cy0, dinv0;      // coefficients of a regular point (NB_REG): all faces open, no wall, no mask nearby
@@ -132,6 +132,7 @@ struct FineLevel {
     __device__ __forceinline__ int pj_off() const { return F.pj_off; }
     __device__ __forceinline__ bool owned(int j) const { return j >= F.jo0 && j < F.jo1; }
     __device__ __forceinline__ long row(int j) const {
+        if (F.periodic_y) j = wrap_col(j, F.ny);
         int aj = F.oj + j;
         if (j < 0 || j >= F.ny || aj < 0 || aj >= F.n2) return -1;
         return (long)aj * F.n1 + F.oi;
@@ -162,6 +163,7 @@ struct CoarseLevel {
     __device__ __forceinline__ int pj_off() const { return A.pj_off; }
     __device__ __forceinline__ bool owned(int j) const { return true; }
     __device__ __forceinline__ long row(int j) const {
+        if (A.periodic_y) j = wrap_col(j, A.ny);
         if (j < 0 || j >= A.ny) return -1;
         return (long)(j + 1) * A.pitch + 1;
     }
@@ -584,6 +586,7 @@ __device__ __forceinline__ void down_body(Window<T, FINE, WJ> &W, const Lev &L, 
             int a = H + warp + r * TILE_WARPS;
             if (a >= WJ - H) break;
             int rp = (par0 + a) & 1, j = wj0 + a;
+            if (j >= L.ny()) continue;             // (y-periodic images are another tile's)
             long rb = L.row(j);
             if (rb < 0) continue;
 #pragma unroll
@@ -711,6 +714,7 @@ k_mg_down(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__
 struct UpArgs {
     int nyc, nxc, pitchc, periodic_c;
     int allow_open;
+    int periodic_yc;
 };
 
 template <typename T, typename TX, typename TF, typename TC, bool FINE, bool DOT, int NU, int WJ, class Lev>
@@ -754,6 +758,7 @@ __device__ __forceinline__ void up_body(Window<T, FINE, WJ> &W, const Lev &L, co
         int a = H + warp + r * TILE_WARPS;
         if (a >= WJ - H) break;
         int rp = (par0 + a) & 1, j = wj0 + a;
+        if (j >= L.ny()) continue;                 // (y-periodic images are another tile's)
         long rb = L.row(j);
         if (rb < 0) continue;
 #pragma unroll
@@ -884,6 +889,7 @@ k_mg_up(Lev L, const TX *__restrict__ xin, TX *__restrict__ xout, const TF *__re
         for (int t = threadIdx.x; t < CJ * CI; t += TILE_THREADS) {
             int a = t / CI, b = t - a * CI;
             int J = Jc0 + a, I = ci0 + b;
+            if (A.periodic_yc) J = wrap_col(J, A.nyc);
             bool ok = J >= 0 && J < A.nyc;
             if (ok) {
                 if (A.periodic_c) I = wrap_col(I, A.nxc);

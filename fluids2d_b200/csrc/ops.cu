@@ -255,12 +255,31 @@ __global__ void k_fill(double *__restrict__ a, int n2, int n1, int nh) {
     else row[n1 - nh + (k - nh)] = row[nh + (k - nh)];
 }
 
+// the same in y for a truly periodic direction (param.ywrap; the reference's yperiodic never
+// wraps, SURVEY note Y): halo rows are copies of the interior rows ny away.  Runs after the
+// x copy and over every column, so the corners are periodic images too.
+__global__ void k_fill_y(double *__restrict__ a, int n2, int n1, int nh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;                      // 0 .. 2 nh - 1
+    if (i >= n1) return;
+    const int ny = n2 - 2 * nh;
+    int j = k < nh ? k : n2 - nh + (k - nh);
+    int src = k < nh ? j + ny : j - ny;
+    a[(size_t)j * n1 + i] = a[(size_t)src * n1 + i];
+}
+
 int op_fill(f2d_ctx *c, double *a) {
-    if (!c->cfg.xperiodic) return F2D_OK;
-    int tot = c->n2 * 2 * c->nh;
-    k_fill<<<(tot + 127) / 128, 128, 0, c->stream>>>(a, c->n2, c->n1, c->nh);
-    c->launches++;
-    F2D_CUDA(cudaGetLastError());
+    if (c->cfg.xperiodic) {
+        int tot = c->n2 * 2 * c->nh;
+        k_fill<<<(tot + 127) / 128, 128, 0, c->stream>>>(a, c->n2, c->n1, c->nh);
+        c->launches++;
+        F2D_CUDA(cudaGetLastError());
+    }
+    if (c->cfg.yperiodic == 2) {
+        k_fill_y<<<dim3((c->n1 + 127) / 128, 2 * c->nh), 128, 0, c->stream>>>(a, c->n2, c->n1, c->nh);
+        c->launches++;
+        F2D_CUDA(cudaGetLastError());
+    }
     return F2D_OK;
 }
 

@@ -722,6 +722,17 @@ __global__ void k_fill_many(FillMany f, int n2, int n1, int nh) {
     }
 }
 
+// y copy of the same arrays for a truly periodic y direction (param.ywrap; after the x copy)
+__global__ void k_fill_many_y(FillMany f, int n2, int n1, int nh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (i >= n1) return;
+    const int ny = n2 - 2 * nh;
+    int j = k < nh ? k : n2 - nh + (k - nh);
+    int src = k < nh ? j + ny : j - ny;
+    for (int q = 0; q < f.n; q++) f.a[q][(size_t)j * n1 + i] = f.a[q][(size_t)src * n1 + i];
+}
+
 // ---------------------------------------------------------------------------
 // qg_projection of the tendency (operators.py:176-211), anomaly form
 // ---------------------------------------------------------------------------
@@ -860,6 +871,32 @@ k_maxabs(long n, const double *__restrict__ ux, const double *__restrict__ uy, d
         (c)->launches++;                \
         F2D_CUDA(cudaGetLastError());   \
     } while (0)
+
+// mesh.fill of up to six arrays: the x-periodic halo copy (skipped when the producing kernel
+// already evaluated the halo columns at their periodic image) and, for param.ywrap, the y copy
+static int fill_many(f2d_ctx *c, const FillMany &f, bool x_copy = true) {
+    if (f.n == 0) return F2D_OK;
+    if (c->cfg.xperiodic && x_copy) {
+        int tot = c->n2 * 2 * c->nh;
+        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+        LAUNCH_CHECK(c);
+    }
+    if (c->cfg.yperiodic == 2) {
+        k_fill_many_y<<<dim3((c->n1 + 127) / 128, 2 * c->nh), 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
+        LAUNCH_CHECK(c);
+    }
+    return F2D_OK;
+}
+static int fill_leaves(f2d_ctx *c, const std::vector<std::string> &names, const std::string &prefix = "") {
+    if (c->cfg.yperiodic != 2) return F2D_OK;       // (the element-wise updates keep x-periodic halos consistent)
+    FillMany f;
+    f.n = 0;
+    for (const std::string &nm : names) {
+        f.a[f.n++] = c->f(prefix + nm);
+        if (f.n == 6) { F2D_TRY(fill_many(c, f)); f.n = 0; }
+    }
+    return fill_many(c, f);
+}
 
 template <int MODEL, int NC = 0>
 static int launch_rhs_mom(f2d_ctx *c, double *dux, double *duy, RkFuse rk = RkFuse()) {
@@ -1149,7 +1186,7 @@ int model_addto(f2d_ctx *c, int ncoef, const double *coefs) {
         else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, c0, c1, c2);
         LAUNCH_CHECK(c);
     }
-    return F2D_OK;
+    return fill_leaves(c, c->prognostic);
 }
 
 template <bool PROJECT, int MODEL>
@@ -1178,16 +1215,11 @@ static int launch_diag(f2d_ctx *c, const double *uxin, const double *uyin, int m
 
 static int fill_diag_outputs(f2d_ctx *c) {
     c->U_stale = true;          // U = sharp(u) is formed on demand (ensure_U)
-    if (c->cfg.xperiodic) {
-        FillMany f;
-        f.n = 4;
-        const char *names[4] = {"u.x", "u.y", "omega", "ke"};
-        for (int q = 0; q < 4; q++) f.a[q] = c->f(names[q]);
-        int tot = c->n2 * 2 * c->nh;
-        k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
-        LAUNCH_CHECK(c);
-    }
-    return F2D_OK;
+    FillMany f;
+    f.n = 4;
+    const char *names[4] = {"u.x", "u.y", "omega", "ke"};
+    for (int q = 0; q < 4; q++) f.a[q] = c->f(names[q]);
+    return fill_many(c, f);
 }
 
 static bool byte_map(f2d_ctx *c, const uint8_t *base, long rows, long pitch, int bh, int bw, CUtensorMap *out) {
@@ -1366,16 +1398,12 @@ static bool field_map(f2d_ctx *c, const double *base, int bh, int bw, CUtensorMa
     return true;
 }
 
-static int fill_stage_outputs(f2d_ctx *c, double *dux, double *duy, const RkFuse &rk) {
-    if (!c->cfg.xperiodic) return F2D_OK;
+static int fill_stage_outputs(f2d_ctx *c, double *dux, double *duy, const RkFuse &rk, bool x_copy = true) {
     FillMany f;
     f.n = 0;
     if (rk.write_ds) { f.a[f.n++] = dux; f.a[f.n++] = duy; }
     f.a[f.n++] = rk.ubx; f.a[f.n++] = rk.uby;
-    int tot = c->n2 * 2 * c->nh;
-    k_fill_many<<<(tot + 127) / 128, 128, 0, c->stream>>>(f, c->n2, c->n1, c->nh);
-    LAUNCH_CHECK(c);
-    return F2D_OK;
+    return fill_many(c, f, x_copy);
 }
 
 // F2D_STAGE=tma (default where the arrays qualify: even n1) | point (one thread per point,
@@ -1427,7 +1455,10 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
             return fill_stage_outputs(c, dux, duy, rk);
         }
     }
-    if (variant != 2) return launch_rhs_mom<MODEL, NC>(c, dux, duy, rk);
+    if (variant != 2) {
+        F2D_TRY((launch_rhs_mom<MODEL, NC>(c, dux, duy, rk)));
+        return fill_stage_outputs(c, dux, duy, rk, false);     // the kernel evaluated the x halo at its periodic image
+    }
     dim3 grd((c->n1 + DTX - 1) / DTX, (c->n2 + DTY - 1) / DTY), blk(DTX, 4);
 #define ST_ARGS g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"), b, c->m("ov.x"), c->m("ov.y"), \
                 c->m("mskx"), c->m("msky"), 0.5 * c->dy, dux, duy, rk
@@ -1483,7 +1514,7 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
         else k_addto<3><<<grd, 256, 0, c->stream>>>(n, y, x0, x1, x2, co[0], co[1], co[2]);
         LAUNCH_CHECK(c);
         if (c->dist.on) F2D_TRY(dist_exchange1(c, y, (size_t)c->n1 * sizeof(double), c->n2, 0));
-        return F2D_OK;
+        return fill_leaves(c, {leaf});
     };
     if (bouss) F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
     if (c->tracer) F2D_TRY(tracer_rhs(c, s));
@@ -1533,6 +1564,7 @@ int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma) {
                                            c->f(dsname(2, leaf.c_str())), dt, gamma, first);
         LAUNCH_CHECK(c);
     }
+    F2D_TRY(fill_leaves(c, c->prognostic));
     return model_diag(c);
 }
 

@@ -59,7 +59,7 @@ class Mesh:
         nh = self.param.halowidth
         self.msk = self._allocate()
         xs = slice(None) if self.param.xperiodic else slice(nh, -nh)
-        ys = slice(None) if self.param.yperiodic else slice(nh, -nh)
+        ys = slice(None) if (self.param.yperiodic or getattr(self.param, "ywrap", False)) else slice(nh, -nh)
         if self.slab.nranks > 1:
             # rows of the global default mask that fall in this rank's window
             g = np.zeros((self.ny + 2 * nh, self.shape[1]), dtype="i1")
@@ -112,7 +112,10 @@ def get_shape(param):
 
 
 def fill_halo_array(param, array):
+    n = param.halowidth
     if param.xperiodic:
-        n = param.halowidth
         array[..., :n] = array[..., -2 * n:-n]
         array[..., -n:] = array[..., n:2 * n]
+    if getattr(param, "ywrap", False):        # NEW: a true periodic y direction (after x: corners are images too)
+        array[..., :n, :] = array[..., -2 * n:-n, :]
+        array[..., -n:, :] = array[..., n:2 * n, :]

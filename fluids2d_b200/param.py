@@ -31,6 +31,9 @@ _REFERENCE_DEFAULTS = dict(
 # NEW: device / elliptic-solver controls (the reference has a direct solve)
 _DEVICE_DEFAULTS = dict(
     device=0,
+    ywrap=False,            # a TRUE periodic y direction: halo rows are images, the Laplacian wraps.  (The
+                            # reference's yperiodic only puts 1 in the mask of the halo rows -- meshes.py:74,
+                            # :135-143, elliptic.py:142 -- and is reproduced as is.)  With xperiodic: doubly periodic.
     rank=0, nranks=1,       # y-slab decomposition: this process's slab out of nranks (slabs.py)
     solver="pcg",           # "pcg": multigrid-preconditioned CG; "mg": plain V-cycles
     solver_rtol=1e-12,      # ||b - A x|| <= rtol ||b||

@@ -56,7 +56,9 @@ typedef struct {
     int32_t model;          /* F2D_MODEL_*                                   */
     int32_t nx, ny, nh;     /* param.nx, param.ny, param.halowidth           */
     double Lx, Ly;
-    int32_t xperiodic, yperiodic;
+    int32_t xperiodic, yperiodic;   /* yperiodic: 1 = the reference's behaviour (the mask of the halo rows is 1,
+                                     * nothing wraps: meshes.py:74, :135-143, elliptic.py:142); 2 = a true
+                                     * periodic direction (halo rows are images, the Laplacian wraps): NEW */
     int32_t noslip;         /* F2D_NOSLIP_* flags                            */
     double f0, g, H;
     int32_t integrator;     /* F2D_INT_*                                     */

@@ -113,7 +113,14 @@ _DEFAULTS = dict(  # param.py:13-59 (only what the hot path reads)
     model="euler", nx=40, ny=40, Lx=1.0, Ly=1.0, xperiodic=False, yperiodic=False,
     halowidth=3, noslip=None, f0=10.0, beta=0.0, g=1, H=1, dt=0.0, cfl=0.9, dtmax=9e99,
     integrator="rk3", compflux="weno", vortexforce="weno", innerproduct="weno",
-    maxorder=6, tracer=None, RAgamma=0.1)
+    maxorder=6, tracer=None, RAgamma=0.1,
+    # NOT in the reference (SURVEY note Y): a truly periodic y direction -- halo rows are images
+    # (Mesh.fill copies rows as it copies columns) and the Laplacian wraps in y the way
+    # elliptic.py:153-160 wraps it in x.  The reference has no such mode, so this extension is
+    # pinned only by symmetry: tests/test_oracle_vs_golden.py runs an x-periodic channel (pinned
+    # against the live reference) and its transpose as a y-periodic channel and demands the
+    # transposed fields.
+    ywrap=False)
 
 
 def make_param(**kw):
@@ -178,7 +185,7 @@ class Mesh:
         if msk is None:
             msk = np.zeros(self.shape, dtype=np.int8)
             xs = slice(None) if param.xperiodic else slice(nh, -nh)
-            ys = slice(None) if param.yperiodic else slice(nh, -nh)
+            ys = slice(None) if (param.yperiodic or param.ywrap) else slice(nh, -nh)
             msk[ys, xs] = 1
         self.msk = np.ascontiguousarray(msk, dtype=np.int8)
         self.hb = 0
@@ -213,10 +220,14 @@ class Mesh:
         if isinstance(a, XY):
             self.fill(a.x)
             self.fill(a.y)
-        elif self.param.xperiodic:
+        else:
             n = self.param.halowidth
-            a[:, :n] = a[:, -2 * n:-n]
-            a[:, -n:] = a[:, n:2 * n]
+            if self.param.xperiodic:
+                a[:, :n] = a[:, -2 * n:-n]
+                a[:, -n:] = a[:, n:2 * n]
+            if self.param.ywrap:           # extension, see _DEFAULTS
+                a[:n, :] = a[-2 * n:-n, :]
+                a[-n:, :] = a[n:2 * n, :]
 
     def xy(self, which="c"):
         nh = self.param.halowidth
@@ -233,12 +244,16 @@ class Mesh:
 def solver_mask(mesh, location):
     """elliptic.py:102-111"""
     msk = mesh.msk if location == "c" else mesh.mskv
-    if not mesh.param.xperiodic:
+    if not (mesh.param.xperiodic or mesh.param.ywrap):
         return msk
     n = mesh.param.halowidth
     m = msk * 1
-    m[:, :n] = 0
-    m[:, -n:] = 0
+    if mesh.param.xperiodic:
+        m[:, :n] = 0
+        m[:, -n:] = 0
+    if mesh.param.ywrap:                   # extension: halo rows are images, not unknowns
+        m[:n, :] = 0
+        m[-n:, :] = 0
     return m
 
 
@@ -262,6 +277,10 @@ def laplacian(mesh, location, maindiag=0.0):
         east[:, nx - 1 - n1:] = G[:, n1][:, None]
     south[1:, :] = G[:-1, :]
     north[:-1, :] = G[1:, :]
+    if mesh.param.ywrap:                   # extension: rows wrap the way elliptic.py:153-160 wraps columns
+        n2 = mesh.param.halowidth
+        south[:n2 + 1, :] = G[-n2 - 1, :][None, :]
+        north[ny - 1 - n2:, :] = G[n2, :][None, :]
     fluid = G > -1
     rows, cols, vals = [], [], []
     offsum = np.zeros((ny, nx))

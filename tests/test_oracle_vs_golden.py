@@ -136,3 +136,35 @@ def _compare(m, ref, case, tag):
             continue   # only written by a plotting callback in the reference
         err = rel_l2(a, b, w)
         assert err < 1e-11, (case, tag, k, err)
+
+
+def test_ywrap_extension_is_the_transpose_of_the_x_periodic_channel(oracle):
+    """param.ywrap (a truly periodic y direction) does not exist in the reference (SURVEY note Y:
+    its yperiodic only sets the mask).  The oracle's extension is pinned by symmetry: an x-periodic
+    channel -- reference behaviour, pinned by the goldens -- and the mirror-image flow in a
+    y-periodic channel (x <-> y, vorticity with the opposite sign) must give transposed fields."""
+    def gaussian(x, y, x0, y0, r):
+        return np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * r ** 2))
+
+    def run(transpose):
+        kw = dict(model="euler", nx=72, ny=40, Lx=1.5, Ly=1.0, xperiodic=True)
+        if transpose:
+            kw = dict(model="euler", nx=40, ny=72, Lx=1.0, Ly=1.5, ywrap=True)
+        m = oracle.Model(oracle.make_param(**kw))
+        xv, yv = m.mesh.xy("v")
+        sign = 1.0
+        if transpose:
+            xv, yv, sign = yv, xv, -1.0
+        om = gaussian(xv, yv, 0.1, 0.4, 0.07) - gaussian(xv, yv, 1.15, 0.55, 0.07)     # straddles the periodic boundary
+        m.state.omega[...] = sign * om * m.mesh.mskv * m.mesh.area
+        oracle.set_uv_from_omega(m.mesh, m.state.omega, m.state.u)
+        m.diag(m.state)
+        return m, [m.step() for _ in range(10)]
+
+    a, da = run(False)
+    b, db = run(True)
+    assert max(abs(x - y) for x, y in zip(da, db)) < 1e-14
+    assert rel_l2(-b.state.omega.T, a.state.omega, a.mesh.mskv) < 1e-12
+    assert rel_l2(b.state.u.y.T, a.state.u.x, a.mesh.mskx) < 1e-12
+    assert rel_l2(b.state.u.x.T, a.state.u.y, a.mesh.msky) < 1e-12
+    assert rel_l2(b.state.ke.T, a.state.ke, a.mesh.msk) < 1e-12
