@@ -354,6 +354,7 @@ def run_ours(args):
         # fixed for the whole run has to respect the CFL limit of the speeds it reaches, O(1)
         dt = min(dt, 0.5 * min(mesh.dx, mesh.dy))
     p.dt = dt                     # identical steps from here on
+    model.time.dt = dt
 
     def barrier():
         eng.sync()

@@ -516,7 +516,10 @@ k_cg_dir_apply(FineView F, const TZ *__restrict__ z, const float *__restrict__ p
 
 // x += alpha p ; r -= alpha L p ; (rr, sum r)          alpha = rz / pq.   L p in fp64 from
 // the fp32 direction; same tiles and thread-to-row map as k_cg_dir_apply.
-__global__ void __launch_bounds__(256, 4)      // 64 registers: at 40 the loaded window was spilled as it arrived
+#ifndef F2D_UPD_CTAS
+#define F2D_UPD_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, F2D_UPD_CTAS)      // 4 -> 64 registers: at 40 (6 CTAs) the loaded window was spilled as it arrived
 k_cg_update_p(FineView F, double *__restrict__ x, double *__restrict__ r, const float *__restrict__ p,
               const double *__restrict__ scal, int rz_slot, double *part, unsigned int *count, double *out,
               const uint8_t *__restrict__ tile_open) {
@@ -1607,124 +1610,19 @@ __device__ __forceinline__ CT tail_offdiag(const TailLevel &L, const TailSm &S, 
     return S.cx[s] * S.x[w] + S.cx[e] * S.x[e] + S.cy[s] * S.x[so] + S.cy[no] * S.x[no];
 }
 
-// A level is walked either by the whole CTA (one warp per row, __syncthreads between phases) or --
-// levels of at most TAIL_WARP_POINTS points -- by warp 0 alone with __syncwarp: the coarsest levels are a
-// chain of ~45 phases on a handful of points, and a 1024-thread barrier per phase was most of the kernel.
-constexpr int TAIL_WARP_POINTS = 64;
-
-template <bool WARP>
-__device__ __forceinline__ void tail_sync() {
-    if (WARP) __syncwarp();
-    else __syncthreads();
-}
-template <bool WARP, class Fn>
-__device__ __forceinline__ void tail_points(const TailLevel &L, Fn fn) {
-    if (WARP) {
-        const int n = L.ny * L.nx;
-        for (int t = threadIdx.x & 31; t < n; t += 32) { int J = t / L.nx; fn(J, t - J * L.nx); }
-    } else {
-        TAIL_LOOP(L) fn(J, I);
-    }
-}
-
-template <bool WARP>
+// (tried: warp 0 alone walking the levels of <= 64 points with __syncwarp instead of 1024-thread barriers --
+// 0.041 ms against 0.033 ms: the serial warp loses more than the ~45 barriers cost)
 __device__ __forceinline__ void tail_relax(const TailLevel &L, CT *sm, int periodic, int color, bool zero) {
     TailSm S = tail_sm(sm, L);
-    auto update = [&](int J, int I) {
-        int s = (J + 1) * L.sp + I + 1;
-        CT di = S.dinv[s];
-        CT a = zero ? CT(0) : tail_offdiag(L, S, periodic, J, I);
-        S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
-    };
-    if (WARP) {
-        tail_points<true>(L, [&](int J, int I) { if (!((I + J + color) & 1)) update(J, I); });
-    } else {
-        // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
-        for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
-            for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) update(J, I);
-    }
-    tail_sync<WARP>();
-}
-
-template <bool WARP>
-__device__ __forceinline__ void tail_clear_x(const TailLevel &L, CT *sm) {
-    TailSm S = tail_sm(sm, L);
-    const int n = (L.ny + 2) * L.sp;
-    for (int t = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x; t < n; t += WARP ? 32 : (int)blockDim.x) S.x[t] = CT(0);
-    tail_sync<WARP>();
-}
-
-// pre-smoothing of level L, residual, restriction into the right-hand side of C
-template <bool WARP>
-__device__ __forceinline__ void tail_down(const TailArgs &A, const TailLevel &L, const TailLevel &C, CT *sm) {
-    const int per = A.periodic;
-    TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
-    tail_clear_x<WARP>(L, sm);
-    for (int s = 0; s < A.nu1; s++) {
-        tail_relax<WARP>(L, sm, per, 0, s == 0);
-        tail_relax<WARP>(L, sm, per, 1, false);
-    }
-    tail_points<WARP>(L, [&](int J, int I) {   // residual / prolongation normaliser
-        int sidx = (J + 1) * L.sp + I + 1;
-        CT di = S.dinv[sidx], res = CT(0);
-        if (di != CT(0)) {
-            CT a = tail_offdiag(L, S, per, J, I);
-            res = (S.b[sidx] - (S.x[sidx] / di - a)) / S.w[sidx];
+    // only the points of this colour are visited: column I = 2k + ((J + color) & 1)
+    for (int J = threadIdx.x >> 5; J < L.ny; J += 32)
+        for (int I = 2 * (threadIdx.x & 31) + ((J + color) & 1); I < L.nx; I += 64) {
+            int s = (J + 1) * L.sp + I + 1;
+            CT di = S.dinv[s];
+            CT a = zero ? CT(0) : tail_offdiag(L, S, periodic, J, I);
+            S.x[s] = (S.b[s] + a) * di;        // di == 0 off the unknowns: stays 0
         }
-        S.r[sidx] = res;
-    });
-    tail_sync<WARP>();
-    tail_points<WARP>(C, [&](int J, int I) {   // restriction R = P^T
-        CT acc = CT(0);
-#pragma unroll
-        for (int a = -1; a <= 2; a++) {
-            int j = 2 * J + a;
-            if (per & 2) { if (j < 0) j += L.ny; else if (j >= L.ny) j -= L.ny; }
-            if (j < 0 || j >= L.ny) continue;
-            CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
-#pragma unroll
-            for (int b = -1; b <= 2; b++) {
-                int i = 2 * I + b;
-                if (per & 1) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
-                if (i < 0 || i >= L.nx) continue;
-                CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
-                acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
-            }
-        }
-        SC.b[(J + 1) * C.sp + I + 1] = acc;
-    });
-    tail_sync<WARP>();
-}
-
-// coarsest level: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
-template <bool WARP>
-__device__ __forceinline__ void tail_coarsest(const TailArgs &A, const TailLevel &L, CT *sm) {
-    tail_clear_x<WARP>(L, sm);
-    for (int s = 0; s < 4 * A.nsw; s++)
-        tail_relax<WARP>(L, sm, A.periodic, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
-}
-
-// prolongation of C's correction onto L, post-smoothing
-template <bool WARP>
-__device__ __forceinline__ void tail_up(const TailArgs &A, const TailLevel &L, const TailLevel &C, CT *sm) {
-    const int per = A.periodic;
-    TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
-    tail_points<WARP>(L, [&](int J, int I) {
-        int sidx = (J + 1) * L.sp + I + 1;
-        if (S.dinv[sidx] == CT(0)) return;      // not an unknown (set-up clears the code where 1/diag is 0)
-        int J0, Jn, I0, In;
-        parents(J, I, J0, Jn, I0, In);
-        if (per & 1) In = wrap_mod(In, C.nx);
-        if (per & 2) Jn = wrap_mod(Jn, C.ny);
-        int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
-        CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
-        S.x[sidx] += v / S.w[sidx];
-    });
-    tail_sync<WARP>();
-    for (int s = 0; s < A.nu2; s++) {
-        tail_relax<WARP>(L, sm, per, 1, false);
-        tail_relax<WARP>(L, sm, per, 0, false);
-    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailArgs Ain) {
@@ -1736,6 +1634,7 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
         reinterpret_cast<int *>(&A)[t] = reinterpret_cast<const int *>(&Ain)[t];
     __syncthreads();
     CT *sm = reinterpret_cast<CT *>(smem_raw);
+    const int per = A.periodic;
     // coefficients of every tail level (halo rows / columns included: the east and
     // north faces of the last column / row live there), and the right-hand side
     // of the first tail level, which comes from the level above
@@ -1754,22 +1653,74 @@ __global__ void __launch_bounds__(1024) k_mg_tail(const __grid_constant__ TailAr
         }
     }
     __syncthreads();
-    // levels [0, nbig) by the CTA, [nbig, nlev) by warp 0
-    int nbig = A.nlev;
-    while (nbig > 0 && A.lev[nbig - 1].ny * A.lev[nbig - 1].nx <= TAIL_WARP_POINTS) nbig--;
-    for (int l = 0; l < nbig; l++) {
-        if (l + 1 < A.nlev) tail_down<false>(A, A.lev[l], A.lev[l + 1], sm);
-        else tail_coarsest<false>(A, A.lev[l], sm);
-    }
-    if (nbig < A.nlev) {      // (the barrier that ended the last CTA phase made b of level nbig visible)
-        if (threadIdx.x < 32) {
-            for (int l = nbig; l < A.nlev - 1; l++) tail_down<true>(A, A.lev[l], A.lev[l + 1], sm);
-            tail_coarsest<true>(A, A.lev[A.nlev - 1], sm);
-            for (int l = A.nlev - 2; l >= nbig; l--) tail_up<true>(A, A.lev[l], A.lev[l + 1], sm);
+    for (int l = 0; l < A.nlev - 1; l++) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
+        __syncthreads();
+        for (int s = 0; s < A.nu1; s++) {
+            tail_relax(L, sm, per, 0, s == 0);
+            tail_relax(L, sm, per, 1, false);
+        }
+        TAIL_LOOP(L) {   // residual / prolongation normaliser
+            int sidx = (J + 1) * L.sp + I + 1;
+            CT di = S.dinv[sidx], res = CT(0);
+            if (di != CT(0)) {
+                CT a = tail_offdiag(L, S, per, J, I);
+                res = (S.b[sidx] - (S.x[sidx] / di - a)) / S.w[sidx];
+            }
+            S.r[sidx] = res;
+        }
+        __syncthreads();
+        TAIL_LOOP(C) {   // restriction R = P^T
+            CT acc = CT(0);
+#pragma unroll
+            for (int a = -1; a <= 2; a++) {
+                int j = 2 * J + a;
+                if (per & 2) { if (j < 0) j += L.ny; else if (j >= L.ny) j -= L.ny; }
+                if (j < 0 || j >= L.ny) continue;
+                CT wy = (a == 0 || a == 1) ? CT(3) : CT(1);
+#pragma unroll
+                for (int b = -1; b <= 2; b++) {
+                    int i = 2 * I + b;
+                    if (per & 1) { if (i < 0) i += L.nx; else if (i >= L.nx) i -= L.nx; }
+                    if (i < 0 || i >= L.nx) continue;
+                    CT wx = (b == 0 || b == 1) ? CT(3) : CT(1);
+                    acc += wy * wx * S.r[(j + 1) * L.sp + i + 1];
+                }
+            }
+            SC.b[(J + 1) * C.sp + I + 1] = acc;
         }
         __syncthreads();
     }
-    for (int l = min(nbig - 1, A.nlev - 2); l >= 0; l--) tail_up<false>(A, A.lev[l], A.lev[l + 1], sm);
+    {   // coarsest: nsw sweeps (R,B) then nsw sweeps (B,R) from zero
+        const TailLevel &L = A.lev[A.nlev - 1];
+        TailSm S = tail_sm(sm, L);
+        for (int t = threadIdx.x; t < (L.ny + 2) * L.sp; t += blockDim.x) S.x[t] = CT(0);
+        __syncthreads();
+        for (int s = 0; s < 4 * A.nsw; s++)
+            tail_relax(L, sm, per, (s < 2 * A.nsw) ? (s & 1) : 1 - (s & 1), s == 0);
+    }
+    for (int l = A.nlev - 2; l >= 0; l--) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        TailSm S = tail_sm(sm, L), SC = tail_sm(sm, C);
+        TAIL_LOOP(L) {
+            int sidx = (J + 1) * L.sp + I + 1;
+            if (S.dinv[sidx] == CT(0)) continue;      // not an unknown (set-up clears the code where 1/diag is 0)
+            int J0, Jn, I0, In;
+            parents(J, I, J0, Jn, I0, In);
+            if (per & 1) In = wrap_mod(In, C.nx);
+            if (per & 2) Jn = wrap_mod(Jn, C.ny);
+            int r0 = (J0 + 1) * C.sp, rn = (Jn + 1) * C.sp;   // halo rows/cols hold 0
+            CT v = CT(9) * SC.x[r0 + I0 + 1] + CT(3) * (SC.x[rn + I0 + 1] + SC.x[r0 + In + 1]) + SC.x[rn + In + 1];
+            S.x[sidx] += v / S.w[sidx];
+        }
+        __syncthreads();
+        for (int s = 0; s < A.nu2; s++) {
+            tail_relax(L, sm, per, 1, false);
+            tail_relax(L, sm, per, 0, false);
+        }
+    }
     {   // the correction of the first tail level goes back to global memory
         const TailLevel &L = A.lev[0];
         TailSm S = tail_sm(sm, L);
