@@ -157,8 +157,11 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
         for (auto &leaf : c->prognostic) F2D_TRY(alloc_field(c, "ds" + std::to_string(k) + "." + leaf));
     F2D_CUDA(cudaMalloc(&c->hb, c->n * sizeof(double)));
     F2D_CUDA(cudaMemsetAsync(c->hb, 0, c->n * sizeof(double), c->stream));
-    if (cfg->model == F2D_MODEL_EULER || cfg->model == F2D_MODEL_BOUSSINESQ)
-        for (int t = 0; t < 2; t++) F2D_CUDA(cudaMalloc(&c->tmp[t], c->n * sizeof(double)));
+    if (cfg->model == F2D_MODEL_EULER || cfg->model == F2D_MODEL_BOUSSINESQ || cfg->model == F2D_MODEL_RSW)
+        for (int t = 0; t < 2; t++) {       // u* of the fused stage kernels
+            F2D_CUDA(cudaMalloc(&c->tmp[t], c->n * sizeof(double)));
+            F2D_CUDA(cudaMemsetAsync(c->tmp[t], 0, c->n * sizeof(double), c->stream));
+        }
     F2D_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
     F2D_CUDA(cudaMemsetAsync(c->d_scal, 0, 64 * sizeof(double), c->stream));
     c->part_capacity = std::max<size_t>(4 * 8192, 4 * (c->n / (40 * 40) + 1024));

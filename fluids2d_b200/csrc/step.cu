@@ -188,6 +188,35 @@ k_divflux(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
     dq[k_out] = d * (double)msk[k];
 }
 
+// ... with the Runge-Kutta update of the advected scalar fused in (rsw stage, fused_stage_rsw):
+// y += ((c0 ds_0) + c1 ds_1) + c2 ds_2 as addto_list does (integrators.py:154-174), the last
+// ds being this tendency; the update is in place because the kernel only reads the fluxes.
+struct RkScalar {
+    double c[3];
+    const double *d[2];     // earlier tendencies
+    double *y;
+    int write_ds;
+};
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_divflux_upd(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
+              const int8_t *__restrict__ msk, double *__restrict__ dq, RkScalar rk) {
+    THREAD_2D(g);
+    double d = 0;
+    if (i <= g.n1 - 2) d = -(fx[k + 1] - fx[k]);
+    if (j <= g.n2 - 2) d -= fy[k + s1] - fy[k];
+    d = d * (double)msk[k];
+    if (rk.write_ds) dq[k_out] = d;
+    double acc;
+    if (NC == 1) acc = rk.c[0] * d;
+    else {
+        acc = rk.c[0] * rk.d[0][k_out];
+        if (NC == 2) acc = acc + rk.c[1] * d;
+        else { acc = acc + rk.c[1] * rk.d[1][k_out]; acc = acc + rk.c[2] * d; }
+    }
+    rk.y[k_out] += acc;
+}
+
 // The tracer tendency (equations.py:217-222) is the same `div` WITHOUT the fill
 // that follows every model-owned scalar: halo columns hold what `div` itself
 // leaves there.  operators.py:105 does not assign the last column, so there the
@@ -1525,6 +1554,67 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
     return model_diag_impl(c, true);
 }
 
+// Rotating shallow water stage with the RK update fused the same way: the momentum
+// kernel leaves u* = u + sum c_i ds_i in tmp[0..1] (neighbouring threads still read u),
+// the flux-divergence kernel updates h in place, then u and u* swap roles (a pointer
+// swap, no copy).  Three k_addto passes per stage (25 % of the 8192^2 step) disappear.
+template <int NC>
+static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
+    RkFuse rk;
+    for (int k = 0; k < 3; k++) rk.c[k] = k < NC ? co[k] : 0.0;
+    for (int k = 0; k < 2; k++) {
+        rk.dx[k] = k < NC - 1 ? c->f(dsname(k, "u.x")) : nullptr;
+        rk.dy[k] = k < NC - 1 ? c->f(dsname(k, "u.y")) : nullptr;
+    }
+    rk.ubx = c->tmp[0]; rk.uby = c->tmp[1];
+    rk.write_ds = s < c->nstages - 1;
+    double *dux = c->f(dsname(s, "u.x")), *duy = c->f(dsname(s, "u.y")), *dh = c->f(dsname(s, "h"));
+    F2D_TRY((launch_rhs_mom<M_RSW, NC>(c, dux, duy, rk)));
+    F2D_TRY(apply_forcing(c, "u.x", rk.write_ds ? dux : nullptr, c->tmp[0], co[NC - 1]));
+    F2D_TRY(apply_forcing(c, "u.y", rk.write_ds ? duy : nullptr, c->tmp[1], co[NC - 1]));
+    // thickness: fluxes from the OLD u (u.x / u.y still are), divergence + update of h in place
+    Grid g = grid_of(c);
+    double *fx = c->f("flx.x"), *fy = c->f("flx.y");
+#define FLX_ARGS g, c->f("u.x"), c->f("u.y"), c->f("h"), c->m("oc.x"), c->m("oc.y"), fx, fy
+    switch (c->cfg.compflux) {
+    case F2D_METHOD_WENO: k_flux<WENO><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_UPWIND: k_flux<UPWIND><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_CENTERED: k_flux<CENTERED><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    case F2D_METHOD_CWENO: k_flux<CWENO><<<grd2d(c), blk2d(), 0, c->stream>>>(FLX_ARGS); break;
+    default: set_error("bad compflux method"); return F2D_ERR_ARG;
+    }
+#undef FLX_ARGS
+    LAUNCH_CHECK(c);
+    RkScalar rs;
+    for (int k = 0; k < 3; k++) rs.c[k] = k < NC ? co[k] : 0.0;
+    for (int k = 0; k < 2; k++) rs.d[k] = k < NC - 1 ? c->f(dsname(k, "h")) : nullptr;
+    rs.y = c->f("h");
+    rs.write_ds = rk.write_ds;
+    k_divflux_upd<NC><<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dh, rs);
+    LAUNCH_CHECK(c);
+    F2D_TRY(apply_forcing(c, "h", rk.write_ds ? dh : nullptr, c->f("h"), co[NC - 1]));
+    if (c->tracer) {
+        F2D_TRY(tracer_rhs(c, s));
+        F2D_TRY(apply_forcing(c, "tracer", c->f(dsname(s, "tracer"))));
+        long n = (long)c->n;
+        unsigned grd = (unsigned)((n + 255) / 256);
+        const double *x0 = c->f(dsname(0, "tracer")), *x1 = NC > 1 ? c->f(dsname(1, "tracer")) : nullptr,
+                     *x2 = NC > 2 ? c->f(dsname(2, "tracer")) : nullptr;
+        k_addto<NC><<<grd, 256, 0, c->stream>>>(n, c->f("tracer"), x0, x1, x2, co[0], NC > 1 ? co[1] : 0.0, NC > 2 ? co[2] : 0.0);
+        LAUNCH_CHECK(c);
+    }
+    // u* becomes u
+    std::swap(c->fields["u.x"], c->tmp[0]);
+    std::swap(c->fields["u.y"], c->tmp[1]);
+    return model_diag_impl(c, false);
+}
+
+static int fused_stage_rsw(f2d_ctx *c, int s, int nc, const double *co) {
+    if (nc == 1) return fused_stage_rsw_nc<1>(c, s, co);
+    if (nc == 2) return fused_stage_rsw_nc<2>(c, s, co);
+    return fused_stage_rsw_nc<3>(c, s, co);
+}
+
 // ---------------------------------------------------------------------------
 // Leap-frog + Robert-Asselin filter (integrators.py:20-53).  scratch = [sb, sa, ds]
 //   first:  sb = s ; sa = s ; s += dt ds
@@ -1568,6 +1658,11 @@ int model_step_lfra(f2d_ctx *c, double dt, int first, double gamma) {
     return model_diag(c);
 }
 
+static bool fuse_rsw_off() {
+    static const bool off = getenv("F2D_RSW_UNFUSED") != nullptr;      // A/B against the addto_list passes
+    return off;
+}
+
 int model_step(f2d_ctx *c, double dt, int nsteps) {
     if (!c->mesh_ready) { set_error("f2d_step before f2d_set_mask"); return F2D_ERR_STATE; }
     if (c->cfg.integrator == F2D_INT_LFRA) { set_error("LFRA steps go through f2d_step_lfra"); return F2D_ERR_STATE; }
@@ -1580,6 +1675,8 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
             int st;
             if (c->cfg.model == F2D_MODEL_EULER || c->cfg.model == F2D_MODEL_BOUSSINESQ)
                 st = fused_stage(c, s, nc, co);
+            else if (c->cfg.model == F2D_MODEL_RSW && c->tmp[0] && !fuse_rsw_off())
+                st = fused_stage_rsw(c, s, nc, co);
             else {
                 st = model_rhs(c, s);
                 if (st == F2D_OK) st = model_addto(c, nc, co);
