@@ -547,7 +547,7 @@ struct StageMaps { CUtensorMap om, ux, uy, ke, b; };
 
 template <int MV, int MODEL, int NC>
 __global__ void __launch_bounds__(256, 4)
-k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restrict__ smask, double halfdy,
+k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restrict__ smask, double halfdy, double fcor,
             double *__restrict__ dux, double *__restrict__ duy, RkFuse rk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -564,13 +564,13 @@ k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restri
     }
     __syncthreads();
     if (tid == 0) {
-        constexpr unsigned bytes = (unsigned)(SOW * SOH * 8 + (MODEL == M_BOUSS ? 4 : 3) * S1W * S1H * 8);
+        constexpr unsigned bytes = (unsigned)(SOW * SOH * 8 + ((MODEL == M_BOUSS || MODEL == M_RSW) ? 4 : 3) * S1W * S1H * 8);
         mbar_expect_tx(&bar, bytes);
         tma_load_2d(&som[0][0], &M.om, i0 - SOX, j0 - SHO, &bar);
         tma_load_2d(&sux[0][0], &M.ux, i0 - S1X, j0 - 1, &bar);
         tma_load_2d(&suy[0][0], &M.uy, i0 - S1X, j0 - 1, &bar);
         tma_load_2d(&ske[0][0], &M.ke, i0 - S1X, j0 - 1, &bar);
-        if (MODEL == M_BOUSS) tma_load_2d(&sbb[0][0], &M.b, i0 - S1X, j0 - 1, &bar);
+        if (MODEL == M_BOUSS || MODEL == M_RSW) tma_load_2d(&sbb[0][0], &M.b, i0 - S1X, j0 - 1, &bar);     // b, or the rsw pressure
     }
     // ---- per-point operands without reuse: plain loads, in flight with the boxes
     constexpr int R = STY / 4;
@@ -616,8 +616,20 @@ k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restri
                                 sux[a1 - 1][b1 + 1] * g.idx2);
             ry = (-recon<MV>(ox, Vm, som[a][b - 2], som[a][b - 1], som[a][b], som[a][b + 1], som[a][b + 2], som[a][b + 3])) * Vm;
         }
+        if (MODEL == M_RSW) {   // Coriolis, not masked in the reference (operators.py:32-39)
+            if (j <= g.n2 - 2 && i >= 1)
+                rx += fcor * (((suy[a1][b1 - 1] * g.idy2 + suy[a1 + 1][b1 - 1] * g.idy2) + suy[a1][b1] * g.idy2) +
+                              suy[a1 + 1][b1] * g.idy2);
+            if (j >= 1 && j <= g.n2 - 2 && i <= g.n1 - 2)
+                ry -= fcor * (((sux[a1 - 1][b1] * g.idx2 + sux[a1 - 1][b1 + 1] * g.idx2) + sux[a1][b1] * g.idx2) +
+                              sux[a1][b1 + 1] * g.idx2);
+        }
         if (i >= 1) rx -= (ske[a1][b1] - ske[a1][b1 - 1]) * mx[r];
         if (j >= 1) ry -= (ske[a1][b1] - ske[a1 - 1][b1]) * my[r];
+        if (MODEL == M_RSW) {   // grad p, p = g (h + hb) / area from the last diag
+            if (i >= 1) rx -= (sbb[a1][b1] - sbb[a1][b1 - 1]) * mx[r];
+            if (j >= 1) ry -= (sbb[a1][b1] - sbb[a1 - 1][b1]) * my[r];
+        }
         if (MODEL == M_BOUSS) {
             if (j >= 1) ry += (halfdy * (sbb[a1][b1] + sbb[a1 - 1][b1])) * my[r];
         }
@@ -1457,11 +1469,12 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
         bool ok = field_map(c, c->f("omega"), SOH, SOW, &M.om) && field_map(c, c->f("u.x"), S1H, S1W, &M.ux) &&
                   field_map(c, c->f("u.y"), S1H, S1W, &M.uy) && field_map(c, c->f("ke"), S1H, S1W, &M.ke);
         if (ok && MODEL == M_BOUSS) ok = field_map(c, b, S1H, S1W, &M.b);
+        else if (ok && MODEL == M_RSW) ok = field_map(c, c->f("p"), S1H, S1W, &M.b);
         else if (ok) M.b = M.ke;
         if (ok) {
-            constexpr size_t smem = SOM_BYTES + (MODEL == M_BOUSS ? 4 : 3) * S1_BYTES;
+            constexpr size_t smem = SOM_BYTES + ((MODEL == M_BOUSS || MODEL == M_RSW) ? 4 : 3) * S1_BYTES;
             dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
-#define TMA_ARGS M, g, c->smask, 0.5 * c->dy, dux, duy, rk
+#define TMA_ARGS M, g, c->smask, 0.5 * c->dy, c->cfg.f0 * c->area * 0.25, dux, duy, rk
 #define TMA_LAUNCH(MV)                                                                                        \
     {                                                                                                         \
         static bool once = false;                                                                             \
@@ -1484,7 +1497,7 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
             return fill_stage_outputs(c, dux, duy, rk);
         }
     }
-    if (variant != 2) {
+    if (variant != 2 || MODEL == M_RSW) {
         F2D_TRY((launch_rhs_mom<MODEL, NC>(c, dux, duy, rk)));
         return fill_stage_outputs(c, dux, duy, rk, false);     // the kernel evaluated the x halo at its periodic image
     }
@@ -1569,7 +1582,7 @@ static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
     rk.ubx = c->tmp[0]; rk.uby = c->tmp[1];
     rk.write_ds = s < c->nstages - 1;
     double *dux = c->f(dsname(s, "u.x")), *duy = c->f(dsname(s, "u.y")), *dh = c->f(dsname(s, "h"));
-    F2D_TRY((launch_rhs_mom<M_RSW, NC>(c, dux, duy, rk)));
+    F2D_TRY((launch_stage_tiled<M_RSW, NC>(c, dux, duy, rk)));      // TMA-fed where the arrays qualify
     F2D_TRY(apply_forcing(c, "u.x", rk.write_ds ? dux : nullptr, c->tmp[0], co[NC - 1]));
     F2D_TRY(apply_forcing(c, "u.y", rk.write_ds ? duy : nullptr, c->tmp[1], co[NC - 1]));
     // thickness: fluxes from the OLD u (u.x / u.y still are), divergence + update of h in place
@@ -1814,7 +1827,7 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
         int n = pass == 0 ? 2 : reps;
         if (pass == 1) F2D_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < n; r++) {
-            if (k == "advection" && proj) {
+            if (k == "advection" && (proj || (model == F2D_MODEL_RSW && c->tmp[0]))) {
                 // stage 2 of rk3, fused with the RK update:
                 // R u.x u.y omega ke ds0.x ds0.y [b], W ds1.x ds1.y ub.x ub.y, packed masks (ov.x ov.y mskx msky in 1 byte)
                 RkFuse rk;
@@ -1822,6 +1835,7 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 rk.dx[0] = c->f("ds0.u.x"); rk.dy[0] = c->f("ds0.u.y"); rk.dx[1] = rk.dy[1] = nullptr;
                 rk.ubx = c->tmp[0]; rk.uby = c->tmp[1]; rk.write_ds = 1;
                 if (model == F2D_MODEL_EULER) F2D_TRY((launch_stage_tiled<M_EULER, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
+                else if (model == F2D_MODEL_RSW) F2D_TRY((launch_stage_tiled<M_RSW, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));     // + p
                 else F2D_TRY((launch_stage_tiled<M_BOUSS, 2>(c, c->f("ds1.u.x"), c->f("ds1.u.y"), rk)));
                 *bytes = npts * ((model == F2D_MODEL_EULER ? 10 : 11) * 8 + 1);     // one packed mask byte (smask)
             } else if (k == "advection") {
