@@ -333,3 +333,37 @@ def test_tma_stage_kernel_gives_the_same_bits_as_the_per_point_kernel(tmp_path):
         res[tag] = np.load(path)
     for k in res["tma"].files:
         assert np.array_equal(res["tma"][k], res["point"][k]), k
+
+
+def test_odd_grid_sizes_fall_back_to_the_per_point_kernels(oracle):
+    """TMA needs a row pitch that is a multiple of 16 bytes: an odd n1 = nx + 6 does not qualify
+    and the stage / projection kernels of the one-thread-per-point path run instead (and the
+    x-periodic multigrid stops coarsening at the first odd nx).  Closed 45 x 37 box with an
+    island, five adaptive steps against the oracle."""
+    import fluids2d_b200 as f2d
+    f2d.Param._quiet = True
+    p = f2d.Param()
+    p.nx, p.ny, p.Lx, p.noslip = 45, 37, 1.2, True
+    model = f2d.Model(p)
+    x, y = model.mesh.xy()
+    model.mesh.msk[(x - 0.7) ** 2 + (y - 0.35) ** 2 < 0.09 ** 2] = 0
+    model.mesh.finalize()
+    xv, yv = model.mesh.xy("v")
+    g = lambda x0, y0: np.exp(-((xv - x0) ** 2 + (yv - y0) ** 2) / (2 * 0.07 ** 2))
+    s = model.state
+    s.omega[...] = (g(0.45, 0.6) - g(0.3, 0.6)) * model.mesh.mskv * model.mesh.area
+    f2d.tools.set_uv_from_omega(model, s.omega, s.u)
+    model.integrator.diag(s)
+    om = oracle.Model(oracle.make_param(nx=45, ny=37, Lx=1.2, noslip=True), msk=model.mesh.msk.copy())
+    o = om.state
+    for a, b in ((o.u.x, s.u.x), (o.u.y, s.u.y), (o.omega, s.omega), (o.ke, s.ke), (o.p, s.p), (o.U.x, s.U.x), (o.U.y, s.U.y)):
+        a[...] = b
+    for _ in range(5):
+        model.set_dt()
+        dt = model.time.dt
+        model.step(1)
+        om.step(dt)
+    for name, a, b, w in (("u.x", s.u.x, o.u.x, model.mesh.mskx), ("u.y", s.u.y, o.u.y, model.mesh.msky),
+                          ("omega", s.omega, o.omega, model.mesh.mskv), ("ke", s.ke, o.ke, model.mesh.msk)):
+        assert rel_l2(a, b, w) <= 1e-10, name
+    model.mesh.engine.close()
