@@ -665,10 +665,14 @@ constexpr size_t DU_BYTES = pad128((size_t)DUW * DUH * 8), DP_BYTES = pad128((si
                  DM_BYTES = pad128((size_t)DMW * DMH);
 struct DiagMaps { CUtensorMap ux, uy, p, m; };
 
-template <int MK>
+// PROJECT = false (rotating shallow water): the velocity boxes are the state's u itself, there is
+// no pressure box and no phase 1; the kernel also writes p = g (h + hb) / area (operators.py:110-111).
+struct DiagRsw { const double *h, *hb; double *p; double g_over_area; };
+
+template <int MK, bool PROJECT>
 __global__ void __launch_bounds__(256, 4)
 k_diag_tma(const __grid_constant__ DiagMaps M, Grid g, double *__restrict__ uxo, double *__restrict__ uyo,
-           double *__restrict__ omega, double *__restrict__ ke) {
+           double *__restrict__ omega, double *__restrict__ ke, DiagRsw rsw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     double(*sux)[DUW] = reinterpret_cast<double(*)[DUW]>(smem_raw);
@@ -683,23 +687,25 @@ k_diag_tma(const __grid_constant__ DiagMaps M, Grid g, double *__restrict__ uxo,
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, (unsigned)(2 * DUW * DUH * 8 + DPW * DPH * 8 + DMW * DMH));
+        mbar_expect_tx(&bar, (unsigned)(2 * DUW * DUH * 8 + (PROJECT ? DPW * DPH * 8 : 0) + DMW * DMH));
         tma_load_2d(&sux[0][0], &M.ux, i0 - 2, j0 - 2, &bar);
         tma_load_2d(&suy[0][0], &M.uy, i0 - 2, j0 - 2, &bar);
-        tma_load_2d(&spp[0][0], &M.p, i0 - 4, j0 - 3, &bar);
+        if (PROJECT) tma_load_2d(&spp[0][0], &M.p, i0 - 4, j0 - 3, &bar);
         tma_load_2d(&smk[0][0], &M.m, i0 - 16, j0 - 2, &bar);
     }
     mbar_wait(&bar, 0);
-    // ---- phase 1: addgrad(p) on the window (operators.py:49-53)
-    for (int t = tid; t < DUW * DUH; t += 256) {
-        const int a = t / DUW, b = t - a * DUW;
-        const int j = j0 - 2 + a, i = i0 - 2 + b;
-        const unsigned m = smk[a][b + 14];
-        const double pc = spp[a + 1][b + 2];
-        if (i >= 1) sux[a][b] -= (pc - spp[a + 1][b + 1]) * (double)(m & 1u);
-        if (j >= 1) suy[a][b] -= (pc - spp[a][b + 2]) * (double)((m >> 1) & 1u);
+    if (PROJECT) {
+        // ---- phase 1: addgrad(p) on the window (operators.py:49-53)
+        for (int t = tid; t < DUW * DUH; t += 256) {
+            const int a = t / DUW, b = t - a * DUW;
+            const int j = j0 - 2 + a, i = i0 - 2 + b;
+            const unsigned m = smk[a][b + 14];
+            const double pc = spp[a + 1][b + 2];
+            if (i >= 1) sux[a][b] -= (pc - spp[a + 1][b + 1]) * (double)(m & 1u);
+            if (j >= 1) suy[a][b] -= (pc - spp[a][b + 2]) * (double)((m >> 1) & 1u);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- phase 2
     constexpr int R = STY / 4;
     const int b = 2 + threadIdx.x, i = i0 + threadIdx.x;
@@ -712,8 +718,12 @@ k_diag_tma(const __grid_constant__ DiagMaps M, Grid g, double *__restrict__ uxo,
         const long k = (long)j * s1 + i;
         const unsigned m = smk[a][b + 14];
         const double ux0 = sux[a][b], uy0 = suy[a][b];
-        uxo[k] = ux0;
-        uyo[k] = uy0;
+        if (PROJECT) {
+            uxo[k] = ux0;
+            uyo[k] = uy0;
+        } else {
+            rsw.p[k] = rsw.g_over_area * (rsw.h[k] + rsw.hb[k]);
+        }
         double om = 0.0;
         if (j >= 1) om = -(ux0 - sux[a - 1][b]);
         if (i >= 1) om += uy0 - suy[a][b - 1];
@@ -1295,10 +1305,10 @@ static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin)
     {                                                                                                                 \
         static bool once = false;                                                                                     \
         if (!once) {                                                                                                  \
-            F2D_CUDA(cudaFuncSetAttribute(k_diag_tma<MKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            F2D_CUDA(cudaFuncSetAttribute(k_diag_tma<MKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             once = true;                                                                                              \
         }                                                                                                             \
-        k_diag_tma<MKV><<<grd, blk, smem, c->stream>>>(M, g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"));   \
+        k_diag_tma<MKV, true><<<grd, blk, smem, c->stream>>>(M, g, c->f("u.x"), c->f("u.y"), c->f("omega"), c->f("ke"), DiagRsw()); \
     }
             switch (c->cfg.innerproduct) {
             case F2D_METHOD_WENO: DT_LAUNCH(0) break;
@@ -1327,6 +1337,47 @@ static int launch_diag_tiled(f2d_ctx *c, const double *uxin, const double *uyin)
 #undef TD_ARGS
     LAUNCH_CHECK(c);
     return fill_diag_outputs(c);
+}
+
+// rotating shallow water: TMA-fed where the arrays qualify (no projection phase), else the per-point kernel.
+// x-periodic halos: the per-point kernel evaluates them at the periodic image, the tiled one fills afterwards.
+static int launch_diag_rsw(f2d_ctx *c) {
+    Grid g = grid_of(c);
+    if (stage_variant() == 0) {
+        DiagMaps M;
+        if (field_map(c, c->f("u.x"), DUH, DUW, &M.ux) && field_map(c, c->f("u.y"), DUH, DUW, &M.uy) &&
+            byte_map(c, c->dmask, c->n2, c->dpitch, DMH, DMW, &M.m)) {
+            M.p = M.ux;
+            constexpr size_t smem = 2 * DU_BYTES + DP_BYTES + DM_BYTES;
+            dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
+            DiagRsw R{c->f("h"), c->hb, c->f("p"), c->cfg.g / c->area};
+#define DR_LAUNCH(MKV)                                                                                                 \
+    {                                                                                                                  \
+        static bool once = false;                                                                                      \
+        if (!once) {                                                                                                   \
+            F2D_CUDA(cudaFuncSetAttribute(k_diag_tma<MKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            once = true;                                                                                               \
+        }                                                                                                              \
+        k_diag_tma<MKV, false><<<grd, blk, smem, c->stream>>>(M, g, nullptr, nullptr, c->f("omega"), c->f("ke"), R);   \
+    }
+            switch (c->cfg.innerproduct) {
+            case F2D_METHOD_WENO: DR_LAUNCH(0) break;
+            case F2D_METHOD_UPWIND: DR_LAUNCH(1) break;
+            case F2D_METHOD_CENTERED: DR_LAUNCH(2) break;
+            case F2D_METHOD_CWENO: DR_LAUNCH(3) break;
+            case F2D_METHOD_CLASSIC: DR_LAUNCH(4) break;
+            default: set_error("bad innerproduct method"); return F2D_ERR_ARG;
+            }
+#undef DR_LAUNCH
+            LAUNCH_CHECK(c);
+            c->U_stale = true;
+            FillMany f;
+            f.n = 3;
+            f.a[0] = c->f("omega"); f.a[1] = c->f("ke"); f.a[2] = c->f("p");
+            return fill_many(c, f);
+        }
+    }
+    return launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct);
 }
 
 // `pre`: the un-projected velocity already sits in tmp[0..1] (fused stage kernel)
@@ -1360,7 +1411,7 @@ static int model_diag_impl(f2d_ctx *c, bool pre) {
         return F2D_OK;
     }
     case F2D_MODEL_RSW:
-        return launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct);
+        return launch_diag_rsw(c);
     case F2D_MODEL_QGRSW:
         return launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1);
     case F2D_MODEL_ADVECTION:

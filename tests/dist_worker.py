@@ -78,6 +78,9 @@ def main():
         got[n] = slabs.gather_global(m.mesh.slab, a, shape_g)
     msk_g = slabs.gather_global(m.mesh.slab, m.mesh.msk, shape_g)
     stats = m.mesh.engine.solver_stats()
+    # the six all-reduced sums behind diagnostics.Bulk (owned rows of every slab)
+    m.integrator.upload(m.state, ["ke", "omega", "U.x", "U.y", "u.x", "u.y"])
+    bulk = m.mesh.engine.bulk_sums()
     out = {"rank": rank, "exchanges": m.mesh.engine.exchange_count(), "solver": stats}
     if rank == 0:
         from util import rel_l2, remove_component_means
@@ -95,6 +98,9 @@ def main():
                 g, a = remove_component_means(g, ref.mesh.msk), remove_component_means(a, ref.mesh.msk)
             w = {"u.x": ref.mesh.mskx, "u.y": ref.mesh.msky, "omega": ref.mesh.mskv}.get(n, ref.mesh.msk)
             errs[n] = rel_l2(g, a, w)
+        ref.integrator.upload(ref.state, ["ke", "omega", "U.x", "U.y", "u.x", "u.y"])
+        bulk_ref = ref.mesh.engine.bulk_sums()
+        errs["bulk_sums"] = float(np.max(np.abs(bulk - bulk_ref) / np.maximum(np.abs(bulk_ref), 1e-300)))
         out["errors"] = errs
         out["ref_solver"] = ref.mesh.engine.solver_stats()
         print("DIST_RESULT " + json.dumps(out), flush=True)
