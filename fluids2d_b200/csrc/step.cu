@@ -1918,9 +1918,9 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
                 *bytes = npts * (7 * 8 + 1);
             } else if (k == "diag" && sw) {
                 // rsw: R u.x u.y h hb, W omega ke p (msk slip ok.x ok.y); qgrsw: R u.x u.y, W omega (slip)
-                if (model == F2D_MODEL_RSW) F2D_TRY((launch_diag<false, M_RSW>(c, c->f("u.x"), c->f("u.y"), c->cfg.innerproduct)));
+                if (model == F2D_MODEL_RSW) F2D_TRY(launch_diag_rsw(c));      // TMA-fed where the arrays qualify
                 else F2D_TRY((launch_diag<false, M_QGRSW>(c, c->f("u.x"), c->f("u.y"), -1)));
-                *bytes = npts * (model == F2D_MODEL_RSW ? 7 * 8 + 4 : 3 * 8 + 1);
+                *bytes = npts * (model == F2D_MODEL_RSW ? 7 * 8 + 1 : 3 * 8 + 1);
             } else if (k == "qg_pv" && model == F2D_MODEL_QGRSW) {
                 // R du.x du.y dh, W pv (slip mskv)
                 k_qg_pv<<<grd2d(c), blk2d(), 0, c->stream>>>(g, c->f("ds1.u.x"), c->f("ds1.u.y"), c->f("ds1.h"), c->m("slip"),
