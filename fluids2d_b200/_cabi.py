@@ -449,7 +449,8 @@ class Engine:
             return 3.0 * iters_per_solve
         if name == "rk_update":
             # the projecting models fuse the velocity update into the tendency kernel
-            return {0: 0, 1: 3, 2: 0, 3: 9}[self.cfg.model]      # rsw: fused as well (step.cu: fused_stage_rsw)
+            # rsw and the Boussinesq buoyancy: fused as well (step.cu: fused_stage_rsw, launch_transport)
+            return {0: 0, 1: 0, 2: 0, 3: 9}[self.cfg.model]
         return 3.0
 
     def bench_kernel(self, name, reps=20):

@@ -158,7 +158,7 @@ int f2d_create(const f2d_config *cfg, f2d_ctx **out) {
     F2D_CUDA(cudaMalloc(&c->hb, c->n * sizeof(double)));
     F2D_CUDA(cudaMemsetAsync(c->hb, 0, c->n * sizeof(double), c->stream));
     if (cfg->model == F2D_MODEL_EULER || cfg->model == F2D_MODEL_BOUSSINESQ || cfg->model == F2D_MODEL_RSW)
-        for (int t = 0; t < 2; t++) {       // u* of the fused stage kernels
+        for (int t = 0; t < ((cfg->model == F2D_MODEL_EULER) ? 2 : 3); t++) {       // u* (and the updated scalar) of the fused stage kernels
             F2D_CUDA(cudaMalloc(&c->tmp[t], c->n * sizeof(double)));
             F2D_CUDA(cudaMemsetAsync(c->tmp[t], 0, c->n * sizeof(double), c->stream));
         }
@@ -194,6 +194,7 @@ int f2d_destroy(f2d_ctx *c) {
     if (c->io_stream) cudaStreamDestroy(c->io_stream);
     cudaFree(c->hb);
     cudaFree(c->smask);
+    cudaFree(c->tmask);
     cudaFree(c->dmask);
     for (double *t : c->tmp) cudaFree(t);
     cudaFree(c->d_scal);

@@ -184,7 +184,8 @@ struct f2d_ctx {
     //   smask (n2, n1):        ov.x/2 | ov.y/2 << 2 | mskx << 4 | msky << 5           (stage kernel: 1 B instead of 4)
     //   dmask (n2, dpitch):    mskx | msky << 1 | msk << 2 | slip << 3 | ok.x/2 << 4 | ok.y/2 << 6
     //                          (diagnostic kernel: 1 B instead of 6; dpitch = n1 rounded up to 16 so that TMA can fetch boxes)
-    uint8_t *smask = nullptr, *dmask = nullptr;
+    //   tmask (n2, n1):        oc.x/2 | oc.y/2 << 2 | msk << 4                        (scalar transport kernel: 1 B instead of 3)
+    uint8_t *smask = nullptr, *dmask = nullptr, *tmask = nullptr;
     int dpitch = 0;
     // TMA tensor maps (128-byte CUtensorMap blobs) of the (n2,n1) arrays, keyed by (base pointer, box)
     struct TmaBlob { alignas(64) unsigned char b[128]; bool ok; };

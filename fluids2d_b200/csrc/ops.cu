@@ -93,7 +93,8 @@ __global__ void k_pack_masks(int n2, int n1, int dpitch, const int8_t *__restric
                              const int8_t *__restrict__ msky, const int8_t *__restrict__ slip,
                              const int8_t *__restrict__ ovx, const int8_t *__restrict__ ovy,
                              const int8_t *__restrict__ okx, const int8_t *__restrict__ oky,
-                             uint8_t *__restrict__ smask, uint8_t *__restrict__ dmask) {
+                             const int8_t *__restrict__ ocx, const int8_t *__restrict__ ocy,
+                             uint8_t *__restrict__ smask, uint8_t *__restrict__ dmask, uint8_t *__restrict__ tmask) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y;
     if (i >= dpitch) return;
@@ -101,6 +102,7 @@ __global__ void k_pack_masks(int n2, int n1, int dpitch, const int8_t *__restric
     if (i < n1) {
         size_t k = (size_t)j * n1 + i;
         smask[k] = (uint8_t)((ovx[k] >> 1) | ((ovy[k] >> 1) << 2) | ((mskx[k] != 0) << 4) | ((msky[k] != 0) << 5));
+        tmask[k] = (uint8_t)((ocx[k] >> 1) | ((ocy[k] >> 1) << 2) | ((msk[k] != 0) << 4));
         d = (uint8_t)((mskx[k] != 0) | ((msky[k] != 0) << 1) | ((msk[k] != 0) << 2) | ((slip[k] != 0) << 3) |
                       ((okx[k] >> 1) << 4) | ((oky[k] >> 1) << 6));
     }
@@ -134,9 +136,10 @@ int build_mesh(f2d_ctx *c, const int8_t *h_msk) {
     c->dpitch = (n1 + 15) & ~15;
     if (!c->smask) F2D_CUDA(cudaMalloc(&c->smask, c->n));
     if (!c->dmask) F2D_CUDA(cudaMalloc(&c->dmask, (size_t)c->dpitch * n2));
+    if (!c->tmask) F2D_CUDA(cudaMalloc(&c->tmask, c->n));
     k_pack_masks<<<dim3((c->dpitch + 127) / 128, n2), 128, 0, c->stream>>>(
         n2, n1, c->dpitch, msk, c->m("mskx"), c->m("msky"), c->m("slip"), c->m("ov.x"), c->m("ov.y"), c->m("ok.x"),
-        c->m("ok.y"), c->smask, c->dmask);
+        c->m("ok.y"), c->m("oc.x"), c->m("oc.y"), c->smask, c->dmask, c->tmask);
     c->launches++;
     F2D_CUDA(cudaGetLastError());
     F2D_CUDA(cudaStreamSynchronize(c->stream));

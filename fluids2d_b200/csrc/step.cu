@@ -188,6 +188,33 @@ k_divflux(Grid g, const double *__restrict__ fx, const double *__restrict__ fy,
     dq[k_out] = d * (double)msk[k];
 }
 
+// ((c0 x0) + c1 x1) + c2 x2 of addto_list (integrators.py:154-174) with the contraction into FMAs
+// spelled out: left to the compiler, WHICH product of c0 x0 + c1 x1 is fused differs from kernel to
+// kernel (measured: 1-ulp differences of b in 1 % of the points between k_addto and the fused
+// transport kernel), and the scalar update must not depend on the kernel that performs it.
+// libf2d_exact.so (-fmad=false) keeps the reference's separately rounded products.
+template <int NC>
+__device__ __forceinline__ double rk_sum(double c0, double c1, double c2, double x0, double x1, double x2) {
+#ifdef F2D_EXACT
+    double acc = c0 * x0;
+    if (NC > 1) acc = acc + c1 * x1;
+    if (NC > 2) acc = acc + c2 * x2;
+    return acc;
+#else
+    double acc = __dmul_rn(c0, x0);
+    if (NC > 1) acc = __fma_rn(c1, x1, acc);
+    if (NC > 2) acc = __fma_rn(c2, x2, acc);
+    return acc;
+#endif
+}
+__device__ __forceinline__ double rk_add(double y, double acc) {
+#ifdef F2D_EXACT
+    return y + acc;
+#else
+    return __dadd_rn(y, acc);
+#endif
+}
+
 // ... with the Runge-Kutta update of the advected scalar fused in (rsw stage, fused_stage_rsw):
 // y += ((c0 ds_0) + c1 ds_1) + c2 ds_2 as addto_list does (integrators.py:154-174), the last
 // ds being this tendency; the update is in place because the kernel only reads the fluxes.
@@ -208,13 +235,10 @@ k_divflux_upd(Grid g, const double *__restrict__ fx, const double *__restrict__ 
     d = d * (double)msk[k];
     if (rk.write_ds) dq[k_out] = d;
     double acc;
-    if (NC == 1) acc = rk.c[0] * d;
-    else {
-        acc = rk.c[0] * rk.d[0][k_out];
-        if (NC == 2) acc = acc + rk.c[1] * d;
-        else { acc = acc + rk.c[1] * rk.d[1][k_out]; acc = acc + rk.c[2] * d; }
-    }
-    rk.y[k_out] += acc;
+    if (NC == 1) acc = rk_sum<1>(rk.c[0], 0, 0, d, 0, 0);
+    else if (NC == 2) acc = rk_sum<2>(rk.c[0], rk.c[1], 0, rk.d[0][k_out], d, 0);
+    else acc = rk_sum<3>(rk.c[0], rk.c[1], rk.c[2], rk.d[0][k_out], rk.d[1][k_out], d);
+    rk.y[k_out] = rk_add(rk.y[k_out], acc);
 }
 
 // The tracer tendency (equations.py:217-222) is the same `div` WITHOUT the fill
@@ -245,10 +269,8 @@ k_addto(long n, double *__restrict__ y, const double *__restrict__ x0,
         double c2) {
     long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    double acc = c0 * x0[k];
-    if (NC > 1) acc = acc + c1 * x1[k];
-    if (NC > 2) acc = acc + c2 * x2[k];
-    y[k] += acc;
+    double acc = rk_sum<NC>(c0, c1, c2, x0[k], NC > 1 ? x1[k] : 0.0, NC > 2 ? x2[k] : 0.0);
+    y[k] = rk_add(y[k], acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -650,6 +672,132 @@ k_stage_tma(const __grid_constant__ StageMaps M, Grid g, const uint8_t *__restri
 }
 
 // ---------------------------------------------------------------------------
+// Transport of a flux-form scalar (rsw thickness, Boussinesq buoyancy), one kernel per RK
+// stage: face fluxes (k_flux, weno.py:346-364), their divergence (k_divflux,
+// operators.py:104-107) and the Runge-Kutta update y* = y + sum c_i ds_i (k_addto /
+// k_divflux_upd), TMA-fed.  The two flux arrays never reach HBM: a thread holds the west and
+// south face fluxes of its 4 consecutive rows in registers, takes the east one from its
+// neighbour lane (SHFL; the last lane of a warp gets it through shared memory from the next warp,
+// or from the 16 threads that evaluate the tile's east edge) and the north one of its top row
+// from the thread above through 2 KB of shared memory (the top quarter of the tile evaluates
+// it): 67 warp-level reconstructions per tile of 64, where letting every warp's last lane
+// evaluate its own east face costs 98.  y* goes to a separate array (neighbouring tiles still read y), the caller swaps the
+// two pointers.  Boxes: q 72 x 22 (columns i0-4 .., rows j0-3 ..), u.x / u.y 68 x 18; the
+// orders and the centre mask come packed in one byte (engine.cuh: tmask).  Algorithmic
+// traffic 6 x 8 + 1 = 49 B/point against (8 x 8 + 3) + 5 x 8 = 107 of the three kernels.
+// ---------------------------------------------------------------------------
+constexpr int TQW = STX + 2 * SOX, TQH = STY + 2 * SHO;
+constexpr size_t TQ_BYTES = pad128((size_t)TQW * TQH * 8);
+struct TransportMaps { CUtensorMap q, ux, uy; };
+struct RkScalarOut {
+    double c[3];
+    const double *d[2];     // earlier tendencies
+    double *ynew;           // y + sum c_i ds_i
+    int write_ds;
+};
+
+template <int MC>
+__device__ __forceinline__ double face_flux_x(const double (*sq)[TQW], const double (*sux)[S1W], int a, int a1, int b,
+                                              int b1, int ox, double idx2) {
+    if (ox <= 0) return 0.0;
+    const double U = sux[a1][b1] * idx2;
+    return recon<MC>(ox, U, sq[a][b - 3], sq[a][b - 2], sq[a][b - 1], sq[a][b], sq[a][b + 1], sq[a][b + 2]) * U;
+}
+template <int MC>
+__device__ __forceinline__ double face_flux_y(const double (*sq)[TQW], const double (*suy)[S1W], int a, int a1, int b,
+                                              int b1, int oy, double idy2) {
+    if (oy <= 0) return 0.0;
+    const double U = suy[a1][b1] * idy2;
+    return recon<MC>(oy, U, sq[a - 3][b], sq[a - 2][b], sq[a - 1][b], sq[a][b], sq[a + 1][b], sq[a + 2][b]) * U;
+}
+
+template <int MC, int NC>
+__global__ void __launch_bounds__(256, 4)
+k_transport_tma(const __grid_constant__ TransportMaps M, Grid g, const uint8_t *__restrict__ tmask,
+                double *__restrict__ dq, RkScalarOut rk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double(*sq)[TQW] = reinterpret_cast<double(*)[TQW]>(smem_raw);
+    double(*sux)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + TQ_BYTES);
+    double(*suy)[S1W] = reinterpret_cast<double(*)[S1W]>(smem_raw + TQ_BYTES + S1_BYTES);
+    double(*sfy)[STX] = reinterpret_cast<double(*)[STX]>(smem_raw + TQ_BYTES + 2 * S1_BYTES);
+    double(*sfe)[2] = reinterpret_cast<double(*)[2]>(smem_raw + TQ_BYTES + 2 * S1_BYTES + 4 * STX * 8);
+    const int i0 = blockIdx.x * STX, j0 = blockIdx.y * STY;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (unsigned)(TQW * TQH * 8 + 2 * S1W * S1H * 8));
+        tma_load_2d(&sq[0][0], &M.q, i0 - SOX, j0 - SHO, &bar);
+        tma_load_2d(&sux[0][0], &M.ux, i0 - S1X, j0 - 1, &bar);
+        tma_load_2d(&suy[0][0], &M.uy, i0 - S1X, j0 - 1, &bar);
+    }
+    // ---- per-point operands: plain loads, in flight with the boxes
+    constexpr int R = STY / 4;
+    const int i = i0 + threadIdx.x;
+    const int jb = j0 + R * threadIdx.y;
+    const long s1 = g.n1;
+    const bool col_ok = i < g.n1;
+    const bool east_lane = (threadIdx.x & 31) == 31;          // its east face belongs to the next warp / tile
+    const bool edge_thread = tid < STY;                        // evaluates the east face of the tile's last column, row tid
+    unsigned mk[R], mn = 0, me = 0;
+    double d0[R], d1[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = jb + r;
+        const bool ok = col_ok && j < g.n2;
+        const long k = ok ? (long)j * s1 + i : 0;
+        mk[r] = ok ? tmask[k] : 0u;                            // oc.x/2 | oc.y/2 << 2 | msk << 4
+        d0[r] = d1[r] = 0.0;
+        if (NC >= 2 && ok) d0[r] = rk.d[0][k];
+        if (NC >= 3 && ok) d1[r] = rk.d[1][k];
+    }
+    if (threadIdx.y == 3 && col_ok && jb + R < g.n2) mn = tmask[(long)(jb + R) * s1 + i];
+    if (edge_thread && j0 + tid < g.n2 && i0 + STX < g.n1) me = tmask[(long)(j0 + tid) * s1 + i0 + STX];
+    mbar_wait(&bar, 0);
+    const int b = SOX + threadIdx.x, b1 = S1X + threadIdx.x;
+    double fxw[R], fys[R + 1];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int a = SHO + R * threadIdx.y + r, a1 = 1 + R * threadIdx.y + r;
+        fxw[r] = face_flux_x<MC>(sq, sux, a, a1, b, b1, (int)((mk[r] & 3u) << 1), g.idx2);
+        fys[r] = face_flux_y<MC>(sq, suy, a, a1, b, b1, (int)(((mk[r] >> 2) & 3u) << 1), g.idy2);
+    }
+    sfy[threadIdx.y][threadIdx.x] = fys[0];
+    if (threadIdx.x == 32) {
+#pragma unroll
+        for (int r = 0; r < R; r++) sfe[R * threadIdx.y + r][0] = fxw[r];
+    }
+    if (edge_thread)
+        sfe[tid][1] = face_flux_x<MC>(sq, sux, SHO + tid, 1 + tid, SOX + STX, S1X + STX, (int)((me & 3u) << 1), g.idx2);
+    __syncthreads();
+    if (threadIdx.y < 3) fys[R] = sfy[threadIdx.y + 1][threadIdx.x];
+    else fys[R] = face_flux_y<MC>(sq, suy, SHO + STY, 1 + STY, b, b1, (int)(((mn >> 2) & 3u) << 1), g.idy2);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = jb + r;
+        const int a = SHO + R * threadIdx.y + r;
+        double fxe = __shfl_down_sync(0xffffffffu, fxw[r], 1);
+        if (east_lane) fxe = sfe[R * threadIdx.y + r][threadIdx.x >> 5];
+        if (!col_ok || j >= g.n2) continue;
+        const long k = (long)j * s1 + i;
+        double d = 0;
+        if (i <= g.n1 - 2) d = -(fxe - fxw[r]);
+        if (j <= g.n2 - 2) d -= fys[r + 1] - fys[r];
+        d = d * (double)((mk[r] >> 4) & 1u);
+        if (rk.write_ds) dq[k] = d;
+        double acc;
+        if (NC == 1) acc = rk_sum<1>(rk.c[0], 0, 0, d, 0, 0);
+        else if (NC == 2) acc = rk_sum<2>(rk.c[0], rk.c[1], 0, d0[r], d, 0);
+        else acc = rk_sum<3>(rk.c[0], rk.c[1], rk.c[2], d0[r], d1[r], d);
+        rk.ynew[k] = rk_add(sq[a][b], acc);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // The projection + diagnostics of the projecting models, TMA-fed (k_diag_tiled's
 // arithmetic, bit for bit).  Boxes: the un-projected u.x, u.y (70 x 21), p (72 x 22)
 // and the packed mask byte (96 x 21, engine.cuh: dmask) of a 64 x 16 tile with the
@@ -669,8 +817,11 @@ struct DiagMaps { CUtensorMap ux, uy, p, m; };
 // no pressure box and no phase 1; the kernel also writes p = g (h + hb) / area (operators.py:110-111).
 struct DiagRsw { const double *h, *hb; double *p; double g_over_area; };
 
+#ifndef F2D_DIAG_CTAS
+#define F2D_DIAG_CTAS 4
+#endif
 template <int MK, bool PROJECT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, F2D_DIAG_CTAS)
 k_diag_tma(const __grid_constant__ DiagMaps M, Grid g, double *__restrict__ uxo, double *__restrict__ uyo,
            double *__restrict__ omega, double *__restrict__ ke, DiagRsw rsw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1567,6 +1718,63 @@ static int launch_stage_tiled(f2d_ctx *c, double *dux, double *duy, const RkFuse
     return fill_stage_outputs(c, dux, duy, rk);
 }
 
+// One-kernel transport of the model's flux-form scalar `leaf` for RK stage s (k_transport_tma):
+// ds_s.leaf and y* = leaf + sum c_i ds_i.leaf, the latter in tmp[2]; *done = false (nothing
+// launched) where TMA does not apply (odd n1, F2D_STAGE=point), the caller then takes the
+// flux / divergence / update kernels.  The caller swaps fields[leaf] and tmp[2] once nothing
+// reads the old scalar any more.
+template <int NC>
+static int launch_transport(f2d_ctx *c, const std::string &leaf, int s, const double *co, bool *done) {
+    *done = false;
+    if (stage_variant() != 0 || !c->tmp[2] || !c->tmask) return F2D_OK;
+    TransportMaps M;
+    if (!(field_map(c, c->f(leaf), TQH, TQW, &M.q) && field_map(c, c->f("u.x"), S1H, S1W, &M.ux) &&
+          field_map(c, c->f("u.y"), S1H, S1W, &M.uy)))
+        return F2D_OK;
+    RkScalarOut rk;
+    for (int k = 0; k < 3; k++) rk.c[k] = k < NC ? co[k] : 0.0;
+    for (int k = 0; k < 2; k++) rk.d[k] = k < NC - 1 ? c->f(dsname(k, leaf.c_str())) : nullptr;
+    rk.ynew = c->tmp[2];
+    rk.write_ds = s < c->nstages - 1;
+    double *dq = c->f(dsname(s, leaf.c_str()));
+    Grid g = grid_of(c);
+    constexpr size_t smem = TQ_BYTES + 2 * S1_BYTES + 4 * STX * 8 + STY * 2 * 8;
+    dim3 grd((c->n1 + STX - 1) / STX, (c->n2 + STY - 1) / STY), blk(STX, 4);
+#define TR_LAUNCH(MC)                                                                                         \
+    {                                                                                                         \
+        static bool once = false;                                                                             \
+        if (!once) {                                                                                          \
+            F2D_CUDA(cudaFuncSetAttribute(k_transport_tma<MC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            once = true;                                                                                      \
+        }                                                                                                     \
+        k_transport_tma<MC, NC><<<grd, blk, smem, c->stream>>>(M, g, c->tmask, dq, rk);                      \
+    }
+    switch (c->cfg.compflux) {
+    case F2D_METHOD_WENO: TR_LAUNCH(WENO) break;
+    case F2D_METHOD_UPWIND: TR_LAUNCH(UPWIND) break;
+    case F2D_METHOD_CENTERED: TR_LAUNCH(CENTERED) break;
+    case F2D_METHOD_CWENO: TR_LAUNCH(CWENO) break;
+    default: set_error("bad compflux method"); return F2D_ERR_ARG;
+    }
+#undef TR_LAUNCH
+    LAUNCH_CHECK(c);
+    // mesh.fill of the tendency (the reference fills every model-owned ds) and of y*
+    FillMany f;
+    f.n = 0;
+    if (rk.write_ds) f.a[f.n++] = dq;
+    f.a[f.n++] = rk.ynew;
+    F2D_TRY(fill_many(c, f));
+    // forcing: into the stored tendency and, scaled by this stage's own coefficient, into y*
+    F2D_TRY(apply_forcing(c, leaf.c_str(), rk.write_ds ? dq : nullptr, rk.ynew, co[NC - 1]));
+    *done = true;
+    return F2D_OK;
+}
+static int launch_transport(f2d_ctx *c, const std::string &leaf, int s, int nc, const double *co, bool *done) {
+    if (nc == 1) return launch_transport<1>(c, leaf, s, co, done);
+    if (nc == 2) return launch_transport<2>(c, leaf, s, co, done);
+    return launch_transport<3>(c, leaf, s, co, done);
+}
+
 // Euler / Boussinesq stage with the velocity update fused into the tendency
 // kernel: u* = u + sum c_i ds_i lands in tmp[0..1], the projection writes u.
 static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
@@ -1609,11 +1817,17 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
         if (c->dist.on) F2D_TRY(dist_exchange1(c, y, (size_t)c->n1 * sizeof(double), c->n2, 0));
         return fill_leaves(c, {leaf});
     };
-    if (bouss) F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
+    bool b_fused = false;        // buoyancy: flux, divergence and update in one kernel where TMA applies
+    if (bouss) F2D_TRY(launch_transport(c, "b", s, nc, co, &b_fused));
+    if (bouss && !b_fused) F2D_TRY(launch_divflux(c, c->f("b"), c->f(dsname(s, "b"))));
     if (c->tracer) F2D_TRY(tracer_rhs(c, s));
-    if (bouss) F2D_TRY(apply_forcing(c, "b", c->f(dsname(s, "b"))));
+    if (bouss && !b_fused) F2D_TRY(apply_forcing(c, "b", c->f(dsname(s, "b"))));
     if (c->tracer) F2D_TRY(apply_forcing(c, "tracer", c->f(dsname(s, "tracer"))));
-    if (bouss) F2D_TRY(update_scalar("b"));
+    if (bouss && !b_fused) F2D_TRY(update_scalar("b"));
+    if (b_fused) {
+        std::swap(c->fields["b"], c->tmp[2]);          // b* becomes b
+        if (c->dist.on) F2D_TRY(dist_exchange1(c, c->f("b"), (size_t)c->n1 * sizeof(double), c->n2, 0));
+    }
     if (c->tracer) F2D_TRY(update_scalar("tracer"));
     return model_diag_impl(c, true);
 }
@@ -1622,6 +1836,8 @@ static int fused_stage(f2d_ctx *c, int s, int nc, const double *co) {
 // kernel leaves u* = u + sum c_i ds_i in tmp[0..1] (neighbouring threads still read u),
 // the flux-divergence kernel updates h in place, then u and u* swap roles (a pointer
 // swap, no copy).  Three k_addto passes per stage (25 % of the 8192^2 step) disappear.
+template <int NC>
+static int rsw_thickness_unfused(f2d_ctx *c, int s, const double *co, int write_ds, double *dh);
 template <int NC>
 static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
     RkFuse rk;
@@ -1636,7 +1852,30 @@ static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
     F2D_TRY((launch_stage_tiled<M_RSW, NC>(c, dux, duy, rk)));      // TMA-fed where the arrays qualify
     F2D_TRY(apply_forcing(c, "u.x", rk.write_ds ? dux : nullptr, c->tmp[0], co[NC - 1]));
     F2D_TRY(apply_forcing(c, "u.y", rk.write_ds ? duy : nullptr, c->tmp[1], co[NC - 1]));
-    // thickness: fluxes from the OLD u (u.x / u.y still are), divergence + update of h in place
+    // thickness: fluxes from the OLD u (u.x / u.y still are); one kernel where TMA applies (h* in tmp[2]) ...
+    bool h_fused = false;
+    F2D_TRY(launch_transport<NC>(c, "h", s, co, &h_fused));
+    if (!h_fused) F2D_TRY((rsw_thickness_unfused<NC>(c, s, co, rk.write_ds, dh)));
+    if (c->tracer) {
+        F2D_TRY(tracer_rhs(c, s));
+        F2D_TRY(apply_forcing(c, "tracer", c->f(dsname(s, "tracer"))));
+        long n = (long)c->n;
+        unsigned grd = (unsigned)((n + 255) / 256);
+        const double *x0 = c->f(dsname(0, "tracer")), *x1 = NC > 1 ? c->f(dsname(1, "tracer")) : nullptr,
+                     *x2 = NC > 2 ? c->f(dsname(2, "tracer")) : nullptr;
+        k_addto<NC><<<grd, 256, 0, c->stream>>>(n, c->f("tracer"), x0, x1, x2, co[0], NC > 1 ? co[1] : 0.0, NC > 2 ? co[2] : 0.0);
+        LAUNCH_CHECK(c);
+    }
+    // u* becomes u, h* becomes h
+    std::swap(c->fields["u.x"], c->tmp[0]);
+    std::swap(c->fields["u.y"], c->tmp[1]);
+    if (h_fused) std::swap(c->fields["h"], c->tmp[2]);
+    return model_diag_impl(c, false);
+}
+
+// ... else the flux kernel, then divergence + update of h in place
+template <int NC>
+static int rsw_thickness_unfused(f2d_ctx *c, int s, const double *co, int write_ds, double *dh) {
     Grid g = grid_of(c);
     double *fx = c->f("flx.x"), *fy = c->f("flx.y");
 #define FLX_ARGS g, c->f("u.x"), c->f("u.y"), c->f("h"), c->m("oc.x"), c->m("oc.y"), fx, fy
@@ -1653,24 +1892,11 @@ static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
     for (int k = 0; k < 3; k++) rs.c[k] = k < NC ? co[k] : 0.0;
     for (int k = 0; k < 2; k++) rs.d[k] = k < NC - 1 ? c->f(dsname(k, "h")) : nullptr;
     rs.y = c->f("h");
-    rs.write_ds = rk.write_ds;
+    rs.write_ds = write_ds;
     k_divflux_upd<NC><<<grd2d(c), blk2d(), 0, c->stream>>>(g, fx, fy, c->m("msk"), dh, rs);
     LAUNCH_CHECK(c);
-    F2D_TRY(apply_forcing(c, "h", rk.write_ds ? dh : nullptr, c->f("h"), co[NC - 1]));
-    if (c->tracer) {
-        F2D_TRY(tracer_rhs(c, s));
-        F2D_TRY(apply_forcing(c, "tracer", c->f(dsname(s, "tracer"))));
-        long n = (long)c->n;
-        unsigned grd = (unsigned)((n + 255) / 256);
-        const double *x0 = c->f(dsname(0, "tracer")), *x1 = NC > 1 ? c->f(dsname(1, "tracer")) : nullptr,
-                     *x2 = NC > 2 ? c->f(dsname(2, "tracer")) : nullptr;
-        k_addto<NC><<<grd, 256, 0, c->stream>>>(n, c->f("tracer"), x0, x1, x2, co[0], NC > 1 ? co[1] : 0.0, NC > 2 ? co[2] : 0.0);
-        LAUNCH_CHECK(c);
-    }
-    // u* becomes u
-    std::swap(c->fields["u.x"], c->tmp[0]);
-    std::swap(c->fields["u.y"], c->tmp[1]);
-    return model_diag_impl(c, false);
+    (void)s;
+    return apply_forcing(c, "h", write_ds ? dh : nullptr, c->f("h"), co[NC - 1]);
 }
 
 static int fused_stage_rsw(f2d_ctx *c, int s, int nc, const double *co) {
@@ -1898,8 +2124,18 @@ int bench_step_kernel(f2d_ctx *c, const char *name, int reps, float *ms, double 
             } else if (k == "flux_div" && (sw || model == F2D_MODEL_BOUSSINESQ)) {
                 // divflux of the advected scalar, two kernels: R u.x u.y q, W flx.x flx.y (oc.x oc.y);
                 // R flx.x flx.y, W dq (msk)
-                F2D_TRY(launch_divflux(c, c->f(scalar), c->f(dsname(1, scalar))));
-                *bytes = npts * (8 * 8 + 3);
+                // where TMA applies (rsw, boussinesq): the one-kernel transport of stage 2 with zero
+                // coefficients, R u.x u.y q ds0, W ds1 q* (tmask) -- fill kernels included in the time
+                bool fused = false;
+                if (model != F2D_MODEL_QGRSW) {
+                    const double zero[3] = {0.0, 0.0, 0.0};
+                    F2D_TRY(launch_transport<2>(c, scalar, 1, zero, &fused));
+                }
+                if (fused) *bytes = npts * (6 * 8 + 1);
+                else {
+                    F2D_TRY(launch_divflux(c, c->f(scalar), c->f(dsname(1, scalar))));
+                    *bytes = npts * (8 * 8 + 3);
+                }
             } else if (k == "rk_update") {
                 // R u ds0 ds1 ds2, W u (one component; coefficients 0 keep u intact)
                 long n1 = (long)c->n;

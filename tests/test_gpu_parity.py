@@ -311,6 +311,9 @@ for case in ("xper_noslip", "disc_island", "warm_bubble", "lock_exchange", "eule
         e.step(dt, 1)
     for f in ("u.x", "u.y", "omega", "ke", "p"):
         out[case + "/" + f] = e.download(f)
+    for f in ("b", "h"):          # the flux-form scalar of the model (k_transport_tma vs k_flux / k_divflux / k_addto)
+        if f in g.fields("init"):
+            out[case + "/" + f] = e.download(f)
     e.close()
 np.savez(sys.argv[1], **out)
 """
@@ -321,7 +324,8 @@ def test_tma_stage_kernel_gives_the_same_bits_as_the_per_point_kernel(tmp_path):
     outside the array) evaluates the same expressions in the same order as k_rhs_mom
     (one thread per point, guarded global loads): three steps of closed, masked and
     x-periodic euler / boussinesq / rsw cases must agree bit for bit (F2D_STAGE=point selects
-    the old kernels; the projection / diagnostic kernels k_diag_tma vs k_diag_tiled / k_diag ride along)."""
+    the old kernels; the projection / diagnostic kernels k_diag_tma vs k_diag_tiled / k_diag and the
+    one-kernel scalar transport k_transport_tma vs k_flux / k_divflux / k_addto ride along)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
