@@ -248,6 +248,7 @@ static int set_mask_impl(f2d_ctx *c, const int8_t *h_msk) {
         for (auto &kv : c->fields) add(kv.second, c->n2, 0, fb);
         add(c->tmp[0], c->n2, 0, fb);
         add(c->tmp[1], c->n2, 0, fb);
+        add(c->tmp[2], c->n2, 0, fb);
         for (int w = 0; w < 3; w++) {
             Multigrid &M = c->mg[w];
             if (!M.built) continue;

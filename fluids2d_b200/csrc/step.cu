@@ -1866,6 +1866,14 @@ static int fused_stage_rsw_nc(f2d_ctx *c, int s, const double *co) {
         k_addto<NC><<<grd, 256, 0, c->stream>>>(n, c->f("tracer"), x0, x1, x2, co[0], NC > 1 ? co[1] : 0.0, NC > 2 ? co[2] : 0.0);
         LAUNCH_CHECK(c);
     }
+    if (c->dist.on) {
+        // slabs: ghost rows of u* and h* from their owners.  The diagnostics below then run on the whole
+        // local array: omega (u +-2 rows), ke and p are exact on every ghost row the next stage reads
+        // (omega +-3, the others +-1 around the owned rows; G = 8 ghost rows), no exchange of their own.
+        void *a[3] = {c->tmp[0], c->tmp[1], h_fused ? c->tmp[2] : c->f("h")};
+        F2D_TRY(dist_exchange(c, 3, a, (size_t)c->n1 * sizeof(double), c->n2, 0));
+        if (c->tracer) F2D_TRY(dist_exchange1(c, c->f("tracer"), (size_t)c->n1 * sizeof(double), c->n2, 0));
+    }
     // u* becomes u, h* becomes h
     std::swap(c->fields["u.x"], c->tmp[0]);
     std::swap(c->fields["u.y"], c->tmp[1]);
@@ -1967,7 +1975,10 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
                 st = fused_stage(c, s, nc, co);
             else if (c->cfg.model == F2D_MODEL_RSW && c->tmp[0] && !fuse_rsw_off())
                 st = fused_stage_rsw(c, s, nc, co);
-            else {
+            else if (c->dist.on) {
+                set_error("slab mode steps through the fused stage kernels only (euler, boussinesq, rsw)");
+                st = F2D_ERR_UNSUPPORTED;
+            } else {
                 st = model_rhs(c, s);
                 if (st == F2D_OK) st = model_addto(c, nc, co);
                 if (st == F2D_OK) st = model_diag(c);

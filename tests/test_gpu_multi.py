@@ -23,6 +23,9 @@ CASES = {
     "closed_islands": dict(nx=256, ny=256, dt=0.05, steps=4, islands=True, noslip=True),
     "xper_channel": dict(nx=256, ny=192, Lx=2.0, dt=0.05, steps=4, xperiodic=True, noslip=["bottom"]),
     "boussinesq": dict(model="boussinesq", nx=192, ny=128, Lx=1.5, dt=0.02, steps=3, islands=True),
+    # rotating shallow water (no solve in the step): u*, h* exchanged once per RK stage, the diagnostics
+    # computed on the ghost rows; islands straddling the interfaces, topography, adaptive dt
+    "rsw_islands": dict(model="rsw", nx=256, ny=192, Lx=1.0, dt=0.0, dtmax=1.0, f0=10.0, steps=8, islands=True, noslip=True),
     # BASELINE config 2 (bench.py's workload) at 1024^2: four tile levels per slab even on 8 ranks,
     # open-tile kernels, CUDA-graph iterations, the cubic first guess -- ten steps
     "config2_1024": dict(nx=1024, ny=1024, dt=0.0, steps=10, xperiodic=True, turbulence=True),
@@ -52,3 +55,5 @@ def test_slabs_match_single_gpu(name, nproc):
         assert v <= 1e-10, (k, v)
     # the decomposition does not change the convergence of the solver
     assert out["solver"]["niters"] <= out["ref_solver"]["niters"] + out["ref_solver"]["nsolves"]
+    if case.get("model") == "rsw":
+        assert out["solver"]["nsolves"] == 0
