@@ -13,8 +13,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "fluids2d_b200", "libf2d.so")
-# the instantiations the 4096^2 Euler benchmark launches (+ the round-1 per-point stage kernel for comparison)
-HOT = ["k_stage_tma<0, 0, 1>", "k_stage_tma<0, 0, 2>", "k_stage_tma<0, 0, 3>", "k_diag_tma<0>", "k_rhs_mom<0, 0, 2>",
+# the instantiations the 4096^2 Euler benchmark launches (+ the round-1 per-point stage kernel for comparison,
+# the rsw diagnostic kernel and the scalar transport kernel of the rsw / boussinesq configurations)
+HOT = ["k_stage_tma<0, 0, 1>", "k_stage_tma<0, 0, 2>", "k_stage_tma<0, 0, 3>", "k_diag_tma<0, true>", "k_diag_tma<0, false>", "k_transport_tma<0, 2>", "k_rhs_mom<0, 0, 2>",
        "k_mg_down<float, float, double, float, true, true, 2, 64", "k_mg_up<float, float, double, float, true, true, 2, 64",
        "k_mg_down<float, float, float, float, false, true, 2, 64", "k_mg_up<float, float, float, float, false, false, 2, 64",
        "k_cg_dir_apply<float>", "k_cg_update_p", "k_cg_resid_guess", "k_mg_tail", "k_div_u", "k_p2p_exchange"]
