@@ -198,8 +198,10 @@ int f2d_timer_start(f2d_ctx *ctx);
 int f2d_timer_stop(f2d_ctx *ctx, float *ms);
 /* bench.py: time ONE kernel alone (`reps` launches between two events on the
  * context's stream; average ms per launch) and report its algorithmic bytes
- * per launch.  Names: advection, rk_update, divergence, project_diag,
- * mg.down0, mg.up0, mg.down1, mg.up1, mg.tail, cg.dir_apply, cg.update.
+ * per launch.  Names: advection, flux_div (the one-kernel scalar transport of
+ * rsw / boussinesq where TMA applies), rk_update, divergence, project_diag,
+ * diag, qg_pv, qg_back (as the model has them), mg.down0, mg.up0, mg.down1,
+ * mg.up1, mg.tail, cg.dir_apply, cg.update.
  * Clobbers scratch arrays and diagnostics: call it last. */
 int f2d_bench_kernel(f2d_ctx *ctx, const char *name, int reps, float *ms, double *alg_bytes);
 /* ---- y-slab decomposition over several GPUs, one process and one context per
@@ -212,7 +214,8 @@ int f2d_bench_kernel(f2d_ctx *ctx, const char *name, int reps, float *ms, double
  *      NCCL communicator (id from f2d_dist_unique_id on rank 0, passed around
  *      by the host program) and must precede f2d_set_mask.  Afterwards
  *      f2d_step / f2d_solve / f2d_max_abs_U exchange ghost rows and reduce
- *      scalars themselves; state arrays are uploaded / downloaded per slab. */
+ *      scalars themselves; state arrays are uploaded / downloaded per slab.
+ *      Models: euler, boussinesq, rsw (F2D_ERR_UNSUPPORTED otherwise). */
 int f2d_dist_unique_id(char *id128);
 int f2d_dist_init(f2d_ctx *ctx, int rank, int world, const char *id128);
 /* refresh the ghost rows of one field from the owners (after an upload) */
