@@ -380,8 +380,9 @@ int dist_init(f2d_ctx *c, int rank, int world, const char *unique_id) {
         return F2D_ERR_ARG;
     }
     if ((gs && gs != D.G) || (gn && gn != D.G)) { set_error("ghost width must be %d", D.G); return F2D_ERR_ARG; }
-    if (c->cfg.model != F2D_MODEL_EULER && c->cfg.model != F2D_MODEL_BOUSSINESQ && c->cfg.model != F2D_MODEL_RSW) {
-        set_error("slab decomposition is implemented for the euler, boussinesq and rsw models");
+    if (c->cfg.model != F2D_MODEL_EULER && c->cfg.model != F2D_MODEL_BOUSSINESQ && c->cfg.model != F2D_MODEL_RSW &&
+        c->cfg.model != F2D_MODEL_QGRSW) {
+        set_error("slab decomposition is implemented for the euler, boussinesq, rsw and qgrsw models");
         return F2D_ERR_UNSUPPORTED;
     }
     if (c->cfg.yperiodic) { set_error("yperiodic is not supported with slabs"); return F2D_ERR_UNSUPPORTED; }

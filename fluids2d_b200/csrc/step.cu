@@ -1975,10 +1975,15 @@ int model_step(f2d_ctx *c, double dt, int nsteps) {
                 st = fused_stage(c, s, nc, co);
             else if (c->cfg.model == F2D_MODEL_RSW && c->tmp[0] && !fuse_rsw_off())
                 st = fused_stage_rsw(c, s, nc, co);
-            else if (c->dist.on) {
-                set_error("slab mode steps through the fused stage kernels only (euler, boussinesq, rsw)");
+            else if (c->dist.on && c->cfg.model != F2D_MODEL_QGRSW) {
+                set_error("slab mode steps through the fused stage kernels (euler, boussinesq, rsw) or the qgrsw stage");
                 st = F2D_ERR_UNSUPPORTED;
             } else {
+                // qgrsw on slabs needs no message of its own: the vertex Helmholtz solve returns psi with
+                // current ghost rows (mg_solve), k_qg_back REPLACES the tendencies by functions of psi +-1
+                // row (exact 7 ghost rows deep), the point-wise update keeps u and h exact that deep, and the
+                // diagnostics (u +-2) and the raw tendencies (omega +-3, h +-3) then are exact on the owned
+                // rows, which is all the right-hand side of the next solve needs (its residual is exchanged).
                 st = model_rhs(c, s);
                 if (st == F2D_OK) st = model_addto(c, nc, co);
                 if (st == F2D_OK) st = model_diag(c);

@@ -26,6 +26,8 @@ CASES = {
     # rotating shallow water (no solve in the step): u*, h* exchanged once per RK stage, the diagnostics
     # computed on the ghost rows; islands straddling the interfaces, topography, adaptive dt
     "rsw_islands": dict(model="rsw", nx=256, ny=192, Lx=1.0, dt=0.0, dtmax=1.0, f0=10.0, steps=8, islands=True, noslip=True),
+    # the QG-projected shallow water model: one vertex Helmholtz solve per stage, no message besides the solver's
+    "qgrsw_islands": dict(model="qgrsw", nx=256, ny=192, Lx=1.0, dt=0.0, dtmax=1.0, f0=10.0, steps=5, islands=True),
     # BASELINE config 2 (bench.py's workload) at 1024^2: four tile levels per slab even on 8 ranks,
     # open-tile kernels, CUDA-graph iterations, the cubic first guess -- ten steps
     "config2_1024": dict(nx=1024, ny=1024, dt=0.0, steps=10, xperiodic=True, turbulence=True),
