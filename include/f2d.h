@@ -215,7 +215,7 @@ int f2d_bench_kernel(f2d_ctx *ctx, const char *name, int reps, float *ms, double
  *      by the host program) and must precede f2d_set_mask.  Afterwards
  *      f2d_step / f2d_solve / f2d_max_abs_U exchange ghost rows and reduce
  *      scalars themselves; state arrays are uploaded / downloaded per slab.
- *      Models: euler, boussinesq, rsw (F2D_ERR_UNSUPPORTED otherwise). */
+ *      Models: euler, boussinesq, rsw, qgrsw (F2D_ERR_UNSUPPORTED otherwise). */
 int f2d_dist_unique_id(char *id128);
 int f2d_dist_init(f2d_ctx *ctx, int rank, int world, const char *id128);
 /* refresh the ghost rows of one field from the owners (after an upload) */
