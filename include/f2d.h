@@ -111,6 +111,9 @@ int f2d_set_topography(f2d_ctx *ctx, const double *h_hb);
  *      "ds0.u.x", "ds1.h", ... (integrators.py:66-67) ----------------------- */
 int f2d_upload(f2d_ctx *ctx, const char *field, const double *h_src);
 int f2d_download(f2d_ctx *ctx, const char *field, double *h_dst);
+/* device address of a field NOW: the fused stage kernels write u* (h*, b*) and the solves their
+ * solution into other arrays and swap the pointers, so the address is valid until the next
+ * f2d_step / f2d_diag only */
 int f2d_field_ptr(f2d_ctx *ctx, const char *field, double **d_ptr);
 
 /* Model.add_forcing (model.py:121-123; addforcingterm, equations.py:229-238) for
