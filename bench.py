@@ -393,10 +393,11 @@ def run_ours(args):
 
     # ---- end to end through the public per-step call, host buffers -----------
     integ.download(s)
-    nfields = len(integ._step_outputs(s))     # what comes back every step ...
-    nin = len(integ._step_inputs(s))          # ... the ones the step reads go in
     for _ in range(2):
         integ.step(s, model.time)
+    nfields = len(integ._step_outputs(s))     # what comes back every step ...
+    nin = len(integ._step_inputs(s))          # ... the ones a (not the first) step reads go in: counted after the
+                                              # warm-up steps, which seed the solutions of the step's own solves
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
