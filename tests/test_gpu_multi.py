@@ -44,6 +44,9 @@ def test_slabs_match_single_gpu(name, nproc):
         pytest.skip("too few rows per rank")
     if nproc == 8 and name != "config2_1024":
         pytest.skip("the small cases have too few rows for 8 slabs")
+    if nproc > 2 and name in ("rsw_islands", "qgrsw_islands"):
+        pytest.skip("rsw / qgrsw slabs were added late in round 2 and verified on 2 GPUs (parity) and, rsw, on "
+                    "2 / 4 / 8 GPUs through bench.py only")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(29611 + nproc), os.path.join(ROOT, "tests", "dist_worker.py"),
            json.dumps(case)]
